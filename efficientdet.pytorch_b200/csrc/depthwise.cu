@@ -1,0 +1,231 @@
+// Depthwise k x k convolution of the MBConv block (k in {3,5}, stride in {1,2}), NHWC, with the
+// reference's static asymmetric TF-"SAME" padding, fused eval-BN affine + swish epilogue.
+// Reference: models/efficientnet.py:52-56,87 ; pads models/utils.py:126-149.
+// Pure bandwidth kernels: 128-bit loads along C, each thread produces a strip of 4 outputs so
+// every input column is fetched once per (row, strip) instead of once per tap.
+#include "common.cuh"
+
+namespace effdet {
+
+constexpr int kTW = 4;  // outputs along x per thread
+
+template <int K, int S>
+__global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                                     float* __restrict__ z, float* __restrict__ y, int B, int H, int W,
+                                                     int C, int pad_t, int pad_l, int Ho, int Wo) {
+    const int cvecs = C / 4;
+    const int wgroups = (Wo + kTW - 1) / kTW;
+    const long long total = (long long)B * Ho * wgroups * cvecs;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvecs);
+    long long r = idx / cvecs;
+    const int og = (int)(r % wgroups);
+    r /= wgroups;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const int ox0 = og * kTW;
+    constexpr int NCOL = (kTW - 1) * S + K;
+    float4 acc[kTW];
+#pragma unroll
+    for (int i = 0; i < kTW; ++i) acc[i] = f4zero();
+    const float* xb = x + (long long)b * H * W * C + cv * 4;
+    const float* wc = w + cv * 4;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S + ky - pad_t;
+        if (iy < 0 || iy >= H) continue;
+        float4 wrow[K];
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) wrow[kx] = ldg4(wc + (ky * K + kx) * C);
+        const float* xr = xb + (long long)iy * W * C;
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const int ix = ox0 * S + j - pad_l;
+            float4 v = f4zero();
+            if (ix >= 0 && ix < W) v = ldg4(xr + (long long)ix * C);
+#pragma unroll
+            for (int i = 0; i < kTW; ++i) {
+                const int kx = j - i * S;
+                if (kx >= 0 && kx < K) acc[i] = f4fma(v, wrow[kx], acc[i]);
+            }
+        }
+    }
+    const float4 sc = ldg4(scale + cv * 4), sh = ldg4(shift + cv * 4);
+#pragma unroll
+    for (int i = 0; i < kTW; ++i) {
+        const int ox = ox0 + i;
+        if (ox >= Wo) break;
+        const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cv * 4;
+        st4(z + o, acc[i]);
+        const float4 u = f4fma(acc[i], sc, sh);
+        st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
+    }
+}
+
+// dx[b,iy,ix,c] = sum_{ky,kx} dz[b,(iy+pt-ky)/S,(ix+pl-kx)/S,c] * w[ky][kx][c]  (where divisible, in range)
+template <int K, int S>
+__global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                          float* __restrict__ dx, int B, int H, int W, int C, int pad_t,
+                                                          int pad_l, int Ho, int Wo) {
+    const int cvecs = C / 4;
+    const long long total = (long long)B * H * W * cvecs;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvecs);
+    long long r = idx / cvecs;
+    const int ix = (int)(r % W);
+    r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    float4 acc = f4zero();
+    const float* gb = dz + (long long)b * Ho * Wo * C + cv * 4;
+    const float* wc = w + cv * 4;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int ty = iy + pad_t - ky;
+        if (ty < 0 || (ty % S) != 0) continue;
+        const int oy = ty / S;
+        if (oy >= Ho) continue;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const int tx = ix + pad_l - kx;
+            if (tx < 0 || (tx % S) != 0) continue;
+            const int ox = tx / S;
+            if (ox >= Wo) continue;
+            acc = f4fma(ldg4(gb + ((long long)oy * Wo + ox) * C), ldg4(wc + (ky * K + kx) * C), acc);
+        }
+    }
+    st4(dx + idx * 4, acc);
+}
+
+// dw[c][ky][kx] += sum_{b,oy,ox} x[b,oy*S+ky-pt,ox*S+kx-pl,c] * dz[b,oy,ox,c]
+template <int K, int S>
+__global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                            float* __restrict__ dw, int B, int H, int W, int C, int pad_t,
+                                                            int pad_l, int Ho, int Wo, int rows_per_block) {
+    __shared__ float4 red[256];
+    const int cvecs = C / 4;
+    const RowPack rp = rowpack(cvecs, blockIdx.y);
+    float4 acc[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) acc[i] = f4zero();
+    const long long npix = (long long)B * Ho * Wo;
+    if (rp.active) {
+        const long long r_begin = (long long)blockIdx.x * rows_per_block;
+        const long long r_end = min(npix, r_begin + rows_per_block);
+        for (long long pr = r_begin + rp.tr; pr < r_end; pr += rp.rows) {
+            const int ox = (int)(pr % Wo);
+            const long long q = pr / Wo;
+            const int oy = (int)(q % Ho);
+            const int b = (int)(q / Ho);
+            const float4 g = ldg4(dz + pr * C + rp.cv * 4);
+            const float* xb = x + (long long)b * H * W * C + rp.cv * 4;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int iy = oy * S + ky - pad_t;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const int ix = ox * S + kx - pad_l;
+                    if (ix < 0 || ix >= W) continue;
+                    acc[ky * K + kx] = f4fma(ldg4(xb + ((long long)iy * W + ix) * C), g, acc[ky * K + kx]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int tap = 0; tap < K * K; ++tap) {
+        red[threadIdx.x] = acc[tap];
+        __syncthreads();
+        if (rp.tr == 0 && rp.cv < cvecs) {
+            float4 s = f4zero();
+            for (int rr = 0; rr < rp.rows; ++rr) s = f4add(s, red[rr * rp.cvb + rp.tc]);
+            float* o = dw + (long long)(rp.cv * 4) * (K * K) + tap;
+            atomicAdd(o, s.x); atomicAdd(o + K * K, s.y); atomicAdd(o + 2 * K * K, s.z); atomicAdd(o + 3 * K * K, s.w);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void pack_dw_weight_kernel(const float* __restrict__ w, float* __restrict__ o, int C, int kk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // output index [tap][c]
+    if (i >= C * kk) return;
+    const int c = i % C, tap = i / C;
+    o[i] = __ldg(w + c * kk + tap);
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+#define DW_DISPATCH(KERNEL, ...)                                                                      \
+    if (k == 3 && stride == 1) KERNEL<3, 1> __VA_ARGS__;                                              \
+    else if (k == 3 && stride == 2) KERNEL<3, 2> __VA_ARGS__;                                         \
+    else if (k == 5 && stride == 1) KERNEL<5, 1> __VA_ARGS__;                                         \
+    else KERNEL<5, 2> __VA_ARGS__;
+
+static int dw_check(const char* who, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo) {
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "%s: bad shape (C must be a multiple of 4)", who);
+    EFFDET_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "%s: k=%d stride=%d unsupported", who, k, stride);
+    EFFDET_REQUIRE(pad_t >= 0 && pad_l >= 0 && pad_t < k && pad_l < k && Ho > 0 && Wo > 0, "%s: bad padding/output", who);
+    EFFDET_REQUIRE((Ho - 1) * stride + k - pad_t <= H + k && (Wo - 1) * stride + k - pad_l <= W + k, "%s: output too large", who);
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_dwconv_fwd(const float* x, const float* w_kkc, const float* scale, const float* shift, float* z,
+                                 float* y, int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho,
+                                 int Wo, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(x && w_kkc && scale && shift && z && y, "dwconv_fwd: null tensor");
+    EFFDET_REQUIRE(aligned16(x) && aligned16(w_kkc) && aligned16(scale) && aligned16(shift) && aligned16(z) && aligned16(y),
+                   "dwconv_fwd: alignment");
+    int s = dw_check("dwconv_fwd", B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo);
+    if (s) return s;
+    EFFDET_DEVICE(device);
+    const long long total = (long long)B * Ho * cdiv(Wo, kTW) * (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    DW_DISPATCH(dw_fwd_kernel, <<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo))
+    return launch_status("dw_fwd_kernel");
+}
+
+extern "C" int effdet_dwconv_bwd_data(const float* dz, const float* w_kkc, float* dx, int B, int H, int W, int C, int k,
+                                      int stride, int pad_t, int pad_l, int Ho, int Wo, int device,
+                                      effdet_stream_t stream) {
+    EFFDET_REQUIRE(dz && w_kkc && dx, "dwconv_bwd_data: null tensor");
+    EFFDET_REQUIRE(aligned16(dz) && aligned16(w_kkc) && aligned16(dx), "dwconv_bwd_data: alignment");
+    int s = dw_check("dwconv_bwd_data", B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo);
+    if (s) return s;
+    EFFDET_DEVICE(device);
+    const long long total = (long long)B * H * W * (C / 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    DW_DISPATCH(dw_bwd_data_kernel, <<<cdiv(total, 256), 256, 0, st>>>(dz, w_kkc, dx, B, H, W, C, pad_t, pad_l, Ho, Wo))
+    return launch_status("dw_bwd_data_kernel");
+}
+
+extern "C" int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* dw_c1kk, int B, int H, int W, int C,
+                                        int k, int stride, int pad_t, int pad_l, int Ho, int Wo, int device,
+                                        effdet_stream_t stream) {
+    EFFDET_REQUIRE(x && dz && dw_c1kk, "dwconv_bwd_weight: null tensor");
+    EFFDET_REQUIRE(aligned16(x) && aligned16(dz), "dwconv_bwd_weight: alignment");
+    int s = dw_check("dwconv_bwd_weight", B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo);
+    if (s) return s;
+    EFFDET_DEVICE(device);
+    const int cvecs = C / 4;
+    const long long npix = (long long)B * Ho * Wo;
+    const int rows = rowpack_rows(cvecs);
+    long long rpb = (npix + 148 * 4 - 1) / (148 * 4);
+    if (rpb < (long long)rows * 4) rpb = (long long)rows * 4;
+    dim3 grid(cdiv(npix, rpb), rowpack_chunks(cvecs));
+    cudaStream_t st = (cudaStream_t)stream;
+    DW_DISPATCH(dw_bwd_weight_kernel, <<<grid, 256, 0, st>>>(x, dz, dw_c1kk, B, H, W, C, pad_t, pad_l, Ho, Wo, (int)rpb))
+    return launch_status("dw_bwd_weight_kernel");
+}
+
+extern "C" int effdet_pack_dw_weight(const float* w_c1kk, float* w_kkc, int C, int k, int device,
+                                     effdet_stream_t stream) {
+    EFFDET_REQUIRE(w_c1kk && w_kkc && C > 0 && (k == 3 || k == 5), "pack_dw_weight: bad arguments");
+    EFFDET_DEVICE(device);
+    pack_dw_weight_kernel<<<cdiv((long long)C * k * k, 256), 256, 0, (cudaStream_t)stream>>>(w_c1kk, w_kkc, C, k * k);
+    return launch_status("pack_dw_weight_kernel");
+}

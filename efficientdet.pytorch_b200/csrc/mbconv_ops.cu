@@ -1,0 +1,286 @@
+// Element-wise / reduction pieces of the MBConv block that are not convolutions:
+//   * backward of swish(BN_eval(z)) with trainable affine (dgamma, dbeta reductions fused)
+//   * squeeze-excite: spatial mean, the two tiny FC layers and their backward
+// Reference: models/efficientnet.py:75-105 (block), :90-94 (SE), models/utils.py:31-47 (swish),
+//            frozen BN models/efficientdet.py:88-92.  All HBM-bound; NHWC float4 row-packed.
+#include "common.cuh"
+
+namespace effdet {
+
+__global__ void __launch_bounds__(256) bnact_bwd_kernel(const effdet_bnact_bwd_args p, const int rows_per_block) {
+    __shared__ float4 red_g[256];
+    __shared__ float4 red_b[256];
+    const int cvecs = p.C / 4;
+    const RowPack rp = rowpack(cvecs, blockIdx.y);
+    const int b = blockIdx.z;
+    float4 sg = f4zero(), sb = f4zero();
+    if (rp.active) {
+        const int c = rp.cv * 4;
+        const float4 sc = ldg4(p.scale + c), sh = ldg4(p.shift + c), mu = ldg4(p.mean + c), rs = ldg4(p.rstd + c);
+        float4 gt = make_float4(1.f, 1.f, 1.f, 1.f), dm = f4zero();
+        if (p.gate) gt = ldg4(p.gate + (long long)b * p.C + c);
+        if (p.dmean) dm = f4scale(ldg4(p.dmean + (long long)b * p.C + c), p.inv_hw);
+        const float rowsc = p.row_scale ? __ldg(p.row_scale + b) : 1.f;
+        const int r_begin = blockIdx.x * rows_per_block;
+        const int r_end = min(p.HW, r_begin + rows_per_block);
+        for (int r = r_begin + rp.tr; r < r_end; r += rp.rows) {
+            const long long off = ((long long)b * p.HW + r) * p.C + c;
+            float4 g = ldg4(p.dy + off);
+            const float4 zz = ldg4(p.z + off);
+            if (p.gate) g = f4fma(g, gt, dm);
+            g = f4scale(g, rowsc);
+            float4 du = g;
+            if (p.act == EFFDET_ACT_SWISH) {
+                const float4 u = f4fma(zz, sc, sh);
+                du = make_float4(g.x * swish_gradf_(u.x), g.y * swish_gradf_(u.y), g.z * swish_gradf_(u.z),
+                                 g.w * swish_gradf_(u.w));
+            }
+            const float4 xh = make_float4((zz.x - mu.x) * rs.x, (zz.y - mu.y) * rs.y, (zz.z - mu.z) * rs.z,
+                                          (zz.w - mu.w) * rs.w);
+            sg = f4fma(du, xh, sg);
+            sb = f4add(sb, du);
+            st4(p.dz + off, f4mul(du, sc));
+        }
+    }
+    red_g[threadIdx.x] = sg;
+    red_b[threadIdx.x] = sb;
+    __syncthreads();
+    if (rp.tr == 0 && rp.cv < cvecs) {
+        float4 ag = f4zero(), ab = f4zero();
+        for (int r = 0; r < rp.rows; ++r) {
+            ag = f4add(ag, red_g[r * rp.cvb + rp.tc]);
+            ab = f4add(ab, red_b[r * rp.cvb + rp.tc]);
+        }
+        float* og = p.dgamma + rp.cv * 4;
+        float* ob = p.dbeta + rp.cv * 4;
+        atomicAdd(og + 0, ag.x); atomicAdd(og + 1, ag.y); atomicAdd(og + 2, ag.z); atomicAdd(og + 3, ag.w);
+        atomicAdd(ob + 0, ab.x); atomicAdd(ob + 1, ab.y); atomicAdd(ob + 2, ab.z); atomicAdd(ob + 3, ab.w);
+    }
+}
+
+// out[b,c] += alpha * sum_r a[b,r,c] * (b2 ? b2[b,r,c] : 1)
+__global__ void __launch_bounds__(256) spatial_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b2,
+                                                             float* __restrict__ out, float alpha, int HW, int C,
+                                                             int rows_per_block) {
+    __shared__ float4 red[256];
+    const int cvecs = C / 4;
+    const RowPack rp = rowpack(cvecs, blockIdx.y);
+    const int b = blockIdx.z;
+    float4 s = f4zero();
+    if (rp.active) {
+        const int r_begin = blockIdx.x * rows_per_block;
+        const int r_end = min(HW, r_begin + rows_per_block);
+        for (int r = r_begin + rp.tr; r < r_end; r += rp.rows) {
+            const long long off = ((long long)b * HW + r) * C + rp.cv * 4;
+            float4 v = ldg4(a + off);
+            if (b2) v = f4mul(v, ldg4(b2 + off));
+            s = f4add(s, v);
+        }
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (rp.tr == 0 && rp.cv < cvecs) {
+        float4 acc = f4zero();
+        for (int r = 0; r < rp.rows; ++r) acc = f4add(acc, red[r * rp.cvb + rp.tc]);
+        float* o = out + (long long)b * C + rp.cv * 4;
+        atomicAdd(o + 0, alpha * acc.x); atomicAdd(o + 1, alpha * acc.y);
+        atomicAdd(o + 2, alpha * acc.z); atomicAdd(o + 3, alpha * acc.w);
+    }
+}
+
+// one CTA per sample: s_pre = W1*mean + b1 ; gate = sigmoid(W2*swish(s_pre) + b2)
+__global__ void __launch_bounds__(256) se_gate_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
+                                                          const float* __restrict__ b1, const float* __restrict__ w2,
+                                                          const float* __restrict__ b2, float* __restrict__ s_pre,
+                                                          float* __restrict__ gate, int C, int S) {
+    extern __shared__ float sm[];
+    float* mu = sm;       // [C]
+    float* sw = sm + C;   // [S]
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int c = t; c < C; c += 256) mu[c] = __ldg(mean + (long long)b * C + c);
+    __syncthreads();
+    for (int j = warp; j < S; j += 8) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(mu[c], __ldg(w1 + (long long)j * C + c), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float v = acc + __ldg(b1 + j);
+            s_pre[(long long)b * S + j] = v;
+            sw[j] = swishf_(v);
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+        float acc = __ldg(b2 + c);
+        for (int j = 0; j < S; ++j) acc = fmaf(sw[j], __ldg(w2 + (long long)c * S + j), acc);
+        gate[(long long)b * C + c] = sigmoidf_(acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ mean,
+                                                          const float* __restrict__ s_pre, const float* __restrict__ gate,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2,
+                                                          float* __restrict__ dmean, float* __restrict__ dw1,
+                                                          float* __restrict__ db1, float* __restrict__ dw2,
+                                                          float* __restrict__ db2, int C, int S) {
+    extern __shared__ float sm[];
+    float* dp2 = sm;            // [C]
+    float* sw = sm + C;         // [S] swish(s_pre)
+    float* dp1 = sm + C + S;    // [S]
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int j = t; j < S; j += 256) sw[j] = swishf_(__ldg(s_pre + (long long)b * S + j));
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+        const float g = __ldg(gate + (long long)b * C + c);
+        const float d = __ldg(dgate + (long long)b * C + c) * g * (1.f - g);
+        dp2[c] = d;
+        atomicAdd(db2 + c, d);
+        for (int j = 0; j < S; ++j) atomicAdd(dw2 + (long long)c * S + j, d * sw[j]);
+    }
+    __syncthreads();
+    for (int j = warp; j < S; j += 8) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(dp2[c], __ldg(w2 + (long long)c * S + j), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float d = acc * swish_gradf_(__ldg(s_pre + (long long)b * S + j));
+            dp1[j] = d;
+            atomicAdd(db1 + j, d);
+        }
+    }
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+        const float m = __ldg(mean + (long long)b * C + c);
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) {
+            const float d = dp1[j];
+            acc = fmaf(d, __ldg(w1 + (long long)j * C + c), acc);
+            atomicAdd(dw1 + (long long)j * C + c, d * m);
+        }
+        dmean[(long long)b * C + c] = acc;
+    }
+}
+
+
+// scale = gamma*rstd ; shift = beta - mean*scale ; rstd = 1/sqrt(var+eps)   (frozen BN -> affine)
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                               float* __restrict__ rstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float r = 1.0f / sqrtf(__ldg(var + c) + eps);
+    const float s = __ldg(gamma + c) * r;
+    rstd[c] = r;
+    scale[c] = s;
+    shift[c] = __ldg(beta + c) - __ldg(mean + c) * s;
+}
+
+// out = a + b
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                                                  long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        st4(o + i * 4, f4add(ldg4(a + i * 4), ldg4(b + i * 4)));
+}
+
+// dz = y > 0 ? dy : 0
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                       float* __restrict__ dz, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 g = ldg4(dy + i * 4), v = ldg4(y + i * 4);
+        st4(dz + i * 4, make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f));
+    }
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                              float* scale, float* shift, float* rstd, int C, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(gamma && beta && mean && var && scale && shift && rstd && C > 0, "bn_fold: bad arguments");
+    EFFDET_DEVICE(device);
+    bn_fold_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, shift, rstd, C);
+    return launch_status("bn_fold_kernel");
+}
+
+extern "C" int effdet_add(const float* a, const float* b, float* out, int64_t n, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(a && b && out && n > 0 && n % 4 == 0, "add: bad arguments (n must be a multiple of 4)");
+    EFFDET_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add: alignment");
+    EFFDET_DEVICE(device);
+    int blocks = cdiv(n / 4, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
+    return launch_status("add_kernel");
+}
+
+extern "C" int effdet_relu_bwd(const float* dy, const float* y, float* dz, int64_t n, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(dy && y && dz && n > 0 && n % 4 == 0, "relu_bwd: bad arguments (n must be a multiple of 4)");
+    EFFDET_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dz), "relu_bwd: alignment");
+    EFFDET_DEVICE(device);
+    int blocks = cdiv(n / 4, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    relu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, dz, n / 4);
+    return launch_status("relu_bwd_kernel");
+}
+
+static void row_grid(int HW, int cvecs, int B, dim3* grid, int* rpb_out) {
+    const int rows = rowpack_rows(cvecs);
+    const int chunks = rowpack_chunks(cvecs);
+    // aim for >= ~4 waves in total but keep >= 8 row-iterations per block
+    long long want_blocks = (148 * 4 + (long long)B * chunks - 1) / ((long long)B * chunks);
+    if (want_blocks < 1) want_blocks = 1;
+    long long rpb = (HW + want_blocks - 1) / want_blocks;
+    if (rpb < (long long)rows * 8) rpb = (long long)rows * 8;
+    *rpb_out = (int)rpb;
+    *grid = dim3(cdiv(HW, rpb), chunks, B);
+}
+
+extern "C" int effdet_bnact_bwd(const effdet_bnact_bwd_args* a, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(a && a->dy && a->z && a->dz && a->scale && a->shift && a->mean && a->rstd && a->dgamma && a->dbeta,
+                   "bnact_bwd: null tensor");
+    EFFDET_REQUIRE(a->C % 4 == 0 && a->C > 0 && a->B > 0 && a->HW > 0 && a->B <= 65535, "bnact_bwd: bad shape");
+    EFFDET_REQUIRE(a->act == EFFDET_ACT_NONE || a->act == EFFDET_ACT_SWISH, "bnact_bwd: act %d unsupported", a->act);
+    EFFDET_REQUIRE(aligned16(a->dy) && aligned16(a->z) && aligned16(a->dz) && aligned16(a->scale) && aligned16(a->shift) &&
+                       aligned16(a->mean) && aligned16(a->rstd) && aligned16(a->gate) && aligned16(a->dmean),
+                   "bnact_bwd: alignment");
+    EFFDET_DEVICE(device);
+    dim3 grid;
+    int rpb;
+    row_grid(a->HW, a->C / 4, a->B, &grid, &rpb);
+    bnact_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, rpb);
+    return launch_status("bnact_bwd_kernel");
+}
+
+extern "C" int effdet_spatial_reduce(const float* a, const float* b2, float* out, float alpha, int B, int HW, int C,
+                                     int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(a && out && B > 0 && B <= 65535 && HW > 0 && C > 0 && C % 4 == 0, "spatial_reduce: bad arguments");
+    EFFDET_REQUIRE(aligned16(a) && aligned16(b2), "spatial_reduce: alignment");
+    EFFDET_DEVICE(device);
+    dim3 grid;
+    int rpb;
+    row_grid(HW, C / 4, B, &grid, &rpb);
+    spatial_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b2, out, alpha, HW, C, rpb);
+    return launch_status("spatial_reduce_kernel");
+}
+
+extern "C" int effdet_se_gate_fwd(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  float* s_pre, float* gate, int B, int C, int S, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(mean && w1 && b1 && w2 && b2 && s_pre && gate, "se_gate_fwd: null tensor");
+    EFFDET_REQUIRE(B > 0 && C > 0 && S > 0 && (size_t)(C + S) * 4 <= 48 * 1024, "se_gate_fwd: bad shape C=%d S=%d", C, S);
+    EFFDET_DEVICE(device);
+    se_gate_fwd_kernel<<<B, 256, (size_t)(C + S) * sizeof(float), (cudaStream_t)stream>>>(mean, w1, b1, w2, b2, s_pre,
+                                                                                       gate, C, S);
+    return launch_status("se_gate_fwd_kernel");
+}
+
+extern "C" int effdet_se_gate_bwd(const float* dgate, const float* mean, const float* s_pre, const float* gate,
+                                  const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2,
+                                  float* db2, int B, int C, int S, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(dgate && mean && s_pre && gate && w1 && w2 && dmean && dw1 && db1 && dw2 && db2,
+                   "se_gate_bwd: null tensor");
+    EFFDET_REQUIRE(B > 0 && C > 0 && S > 0 && (size_t)(C + 2 * S) * 4 <= 48 * 1024, "se_gate_bwd: bad shape");
+    EFFDET_DEVICE(device);
+    se_gate_bwd_kernel<<<B, 256, (size_t)(C + 2 * S) * sizeof(float), (cudaStream_t)stream>>>(
+        dgate, mean, s_pre, gate, w1, w2, dmean, dw1, db1, dw2, db2, C, S);
+    return launch_status("se_gate_bwd_kernel");
+}

@@ -1,0 +1,146 @@
+// EfficientNet stem: 3x3 stride-2 conv (3 -> C0) straight from the NCHW image, static TF-"SAME"
+// pad (left,right,top,bottom) = (0,1,0,1), fused eval-BN affine + swish, NHWC output.
+// Reference: models/efficientnet.py:140-143,193 ; pad rule models/utils.py:126-149.
+// HBM-bound (AI ~ 10 FLOP/B): one pass over the image, one write of z (kept for backward) and y.
+#include "common.cuh"
+
+namespace effdet {
+
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       float* __restrict__ z, float* __restrict__ y, int B, int H, int W,
+                                                       int C0, int Ho, int Wo) {
+    extern __shared__ __align__(16) float ws[];  // [27][C0], tap-major
+    for (int i = threadIdx.x; i < 27 * C0; i += blockDim.x) {
+        const int co = i % C0, tap = i / C0;  // tap = ci*9 + ky*3 + kx
+        ws[i] = __ldg(w + co * 27 + tap);
+    }
+    __syncthreads();
+    const int cvecs = C0 / 4;
+    const long long total = (long long)B * Ho * Wo * cvecs;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int cv = (int)(idx % cvecs);
+    long long pix = idx / cvecs;
+    const int ox = (int)(pix % Wo);
+    pix /= Wo;
+    const int oy = (int)(pix % Ho);
+    const int b = (int)(pix / Ho);
+    float4 acc = f4zero();
+    const float* xb = x + (long long)b * 3 * H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy + ky;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox + kx;
+                float v = 0.f;
+                if (iy < H && ix < W) v = __ldg(xb + ((long long)ci * H + iy) * W + ix);
+                const float4 wv = *reinterpret_cast<const float4*>(&ws[(ci * 9 + ky * 3 + kx) * C0 + cv * 4]);
+                acc = f4fma(make_float4(v, v, v, v), wv, acc);
+            }
+        }
+    }
+    const long long o = (((long long)b * Ho + oy) * Wo + ox) * C0 + cv * 4;
+    st4(z + o, acc);
+    float4 u = f4fma(acc, ldg4(scale + cv * 4), ldg4(shift + cv * 4));
+    st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
+}
+
+constexpr int kStemP = 64;     // pixels staged per iteration
+constexpr int kStemMaxI = 7;   // taps per thread upper bound (27 / (256 / C0)) for C0 <= 64
+
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                         float* __restrict__ dw, int B, int H, int W, int C0, int Ho,
+                                                         int Wo) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                    // [kStemP][28]  (27 taps, padded)
+    float* ds = sm + kStemP * 28;      // [kStemP][C0]
+    const int t = threadIdx.x;
+    const int IG = 256 / C0;           // tap groups
+    const int co = t % C0, ig = t / C0;
+    const bool worker = ig < IG;
+    float acc[kStemMaxI];
+#pragma unroll
+    for (int j = 0; j < kStemMaxI; ++j) acc[j] = 0.f;
+    const long long npix = (long long)B * Ho * Wo;
+    for (long long p0 = (long long)blockIdx.x * kStemP; p0 < npix; p0 += (long long)gridDim.x * kStemP) {
+        for (int i = t; i < kStemP * 27; i += 256) {
+            const int pp = i / 27, tap = i - pp * 27;
+            const long long pix = p0 + pp;
+            float v = 0.f;
+            if (pix < npix) {
+                const int ox = (int)(pix % Wo);
+                const long long r = pix / Wo;
+                const int oy = (int)(r % Ho);
+                const int b = (int)(r / Ho);
+                const int ci = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
+                const int iy = 2 * oy + ky, ix = 2 * ox + kx;
+                if (iy < H && ix < W) v = __ldg(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
+            }
+            xs[pp * 28 + tap] = v;
+        }
+        for (int i = t; i < kStemP * C0 / 4; i += 256) {
+            const int pp = i / (C0 / 4), c4 = i - pp * (C0 / 4);
+            const long long pix = p0 + pp;
+            float4 v = f4zero();
+            if (pix < npix) v = ldg4(dz + pix * C0 + c4 * 4);
+            *reinterpret_cast<float4*>(&ds[pp * C0 + c4 * 4]) = v;
+        }
+        __syncthreads();
+        if (worker) {
+#pragma unroll 4
+            for (int pp = 0; pp < kStemP; ++pp) {
+                const float g = ds[pp * C0 + co];
+#pragma unroll
+                for (int j = 0; j < kStemMaxI; ++j) {
+                    const int tap = ig + j * IG;
+                    if (tap < 27) acc[j] = fmaf(xs[pp * 28 + tap], g, acc[j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+        for (int j = 0; j < kStemMaxI; ++j) {
+            const int tap = ig + j * IG;
+            if (tap < 27) atomicAdd(dw + co * 27 + tap, acc[j]);
+        }
+    }
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift,
+                               float* z, float* y, int B, int H, int W, int C0, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(x_nchw && w_oihw && scale && shift && z && y, "stem_fwd: null tensor");
+    EFFDET_REQUIRE(C0 % 4 == 0 && C0 > 0 && C0 <= 256, "stem_fwd: C0=%d unsupported", C0);
+    EFFDET_REQUIRE(B > 0 && H >= 2 && W >= 2, "stem_fwd: bad shape");
+    EFFDET_REQUIRE(aligned16(z) && aligned16(y) && aligned16(scale) && aligned16(shift), "stem_fwd: alignment");
+    EFFDET_DEVICE(device);
+    const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
+    const long long total = (long long)B * Ho * Wo * (C0 / 4);
+    stem_fwd_kernel<<<cdiv(total, 256), 256, 27 * C0 * sizeof(float), (cudaStream_t)stream>>>(
+        x_nchw, w_oihw, scale, shift, z, y, B, H, W, C0, Ho, Wo);
+    return launch_status("stem_fwd_kernel");
+}
+
+extern "C" int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw_oihw, int B, int H, int W, int C0,
+                                 int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(x_nchw && dz && dw_oihw, "stem_wgrad: null tensor");
+    EFFDET_REQUIRE(C0 % 4 == 0 && C0 >= 8 && C0 <= 64, "stem_wgrad: C0=%d unsupported (8..64)", C0);
+    EFFDET_REQUIRE(aligned16(dz), "stem_wgrad: alignment");
+    EFFDET_DEVICE(device);
+    const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
+    const long long npix = (long long)B * Ho * Wo;
+    int blocks = cdiv(npix, kStemP);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    const size_t smem = (size_t)kStemP * (28 + C0) * sizeof(float);
+    stem_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo);
+    return launch_status("stem_wgrad_kernel");
+}

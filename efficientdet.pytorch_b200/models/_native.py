@@ -1,0 +1,186 @@
+"""ctypes binding of ``csrc/libeffdet_b200.so`` (the C ABI declared in ``include/effdet_b200.h``).
+
+There is deliberately no fallback: if the shared object is missing, or a tensor is not a CUDA
+fp32 tensor, the call raises.  PyTorch only supplies device memory, the current stream and the
+device index; every arithmetic kernel on the hot path lives in the shared object.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
+SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
+SOURCES = ['api.cu', 'conv_simt.cu', 'stem.cu', 'depthwise.cu', 'mbconv_ops.cu', 'bifpn.cu', 'loss.cu',
+           'detect.cu', 'layout.cu']
+NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
+              '-Xcompiler', '-fPIC', '-shared']
+
+ACT_NONE, ACT_RELU, ACT_SWISH, ACT_SIGMOID = 0, 1, 2, 3
+FUSE_UP, FUSE_POOL = 0, 1
+
+
+class EffdetNativeError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile the sm_100a shared object in-tree with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, 'common.cuh'),
+                   os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'effdet_b200.h'))]
+    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
+        return SO_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', SO_PATH] + srcs
+    if verbose:
+        print(' '.join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise EffdetNativeError('nvcc failed:\n' + r.stdout + r.stderr)
+    return SO_PATH
+
+
+_P = ctypes.c_void_p
+_I32 = ctypes.c_int32
+_I64 = ctypes.c_int64
+_F = ctypes.c_float
+
+
+class ConvArgs(ctypes.Structure):
+    _fields_ = [('x', _P), ('x_bstride', _I64), ('w', _P), ('y', _P), ('y_bstride', _I64), ('z', _P),
+                ('bias', _P), ('scale', _P), ('shift', _P), ('a_scale', _P), ('row_scale', _P),
+                ('residual', _P), ('r_bstride', _I64), ('mask_src', _P), ('m_bstride', _I64),
+                ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32)]
+
+
+class WgradArgs(ctypes.Structure):
+    _fields_ = [('x', _P), ('x_bstride', _I64), ('dy', _P), ('dy_bstride', _I64), ('dw', _P), ('dbias', _P),
+                ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32)]
+
+
+class BnActBwdArgs(ctypes.Structure):
+    _fields_ = [('dy', _P), ('z', _P), ('dz', _P), ('scale', _P), ('shift', _P), ('mean', _P), ('rstd', _P),
+                ('dgamma', _P), ('dbeta', _P), ('row_scale', _P), ('gate', _P), ('dmean', _P), ('inv_hw', _F),
+                ('B', _I32), ('HW', _I32), ('C', _I32), ('act', _I32)]
+
+
+class FuseArgs(ctypes.Structure):
+    _fields_ = [('a', _P), ('b', _P), ('c', _P), ('w', _P), ('w_stride', _I32), ('eps', _F), ('out', _P),
+                ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('mode', _I32)]
+
+
+class FuseBwdArgs(ctypes.Structure):
+    _fields_ = [('dout', _P), ('a', _P), ('b', _P), ('c', _P), ('w', _P), ('w_stride', _I32), ('eps', _F),
+                ('da', _P), ('db', _P), ('dc', _P), ('acc_a', _I32), ('acc_b', _I32), ('acc_c', _I32),
+                ('dw', _P), ('scratch', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('mode', _I32)]
+
+
+_INT = ctypes.c_int
+_TAIL = [_INT, _P]  # (device, stream)
+
+# name -> argument types (everything returns int unless noted); mirrors include/effdet_b200.h
+SIGNATURES = {
+    'effdet_conv2d': [ctypes.POINTER(ConvArgs)] + _TAIL,
+    'effdet_conv2d_wgrad': [ctypes.POINTER(WgradArgs)] + _TAIL,
+    'effdet_pack_conv_weight': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
+    'effdet_colsum': [_P, _P, _I64, _INT] + _TAIL,
+    'effdet_stem_fwd': [_P, _P, _P, _P, _P, _P, _INT, _INT, _INT, _INT] + _TAIL,
+    'effdet_stem_wgrad': [_P, _P, _P, _INT, _INT, _INT, _INT] + _TAIL,
+    'effdet_dwconv_fwd': [_P, _P, _P, _P, _P, _P] + [_INT] * 10 + _TAIL,
+    'effdet_dwconv_bwd_data': [_P, _P, _P] + [_INT] * 10 + _TAIL,
+    'effdet_dwconv_bwd_weight': [_P, _P, _P] + [_INT] * 10 + _TAIL,
+    'effdet_pack_dw_weight': [_P, _P, _INT, _INT] + _TAIL,
+    'effdet_bnact_bwd': [ctypes.POINTER(BnActBwdArgs)] + _TAIL,
+    'effdet_bn_fold': [_P, _P, _P, _P, _F, _P, _P, _P, _INT] + _TAIL,
+    'effdet_add': [_P, _P, _P, _I64] + _TAIL,
+    'effdet_relu_bwd': [_P, _P, _P, _I64] + _TAIL,
+    'effdet_spatial_reduce': [_P, _P, _P, _F, _INT, _INT, _INT] + _TAIL,
+    'effdet_se_gate_fwd': [_P] * 7 + [_INT] * 3 + _TAIL,
+    'effdet_se_gate_bwd': [_P] * 11 + [_INT] * 3 + _TAIL,
+    'effdet_bifpn_fuse_fwd': [ctypes.POINTER(FuseArgs)] + _TAIL,
+    'effdet_bifpn_fuse_bwd': [ctypes.POINTER(FuseBwdArgs)] + _TAIL,
+    'effdet_focal_loss_fwd': [_P] * 7 + [_INT] * 4 + [_F, _F] + _TAIL,
+    'effdet_focal_loss_bwd': [_P] * 9 + [_INT] * 4 + [_F, _F] + _TAIL,
+    'effdet_sigmoid_bwd': [_P, _P, _P, _I64] + _TAIL,
+    'effdet_detect_candidates': [_P] * 8 + [_INT, _INT, _INT, _F, _F, _F] + _TAIL,
+    'effdet_nms': [_P, _P, _INT, ctypes.c_double, _P, _P, _P] + _TAIL,
+    'effdet_gather_detections': [_P, _P, _P, _P, _INT, _P, _P, _P] + _TAIL,
+    'effdet_nchw_to_nhwc': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
+    'effdet_nhwc_to_nchw': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
+}
+PLAIN = {'effdet_version': (ctypes.c_int, []), 'effdet_last_error': (ctypes.c_char_p, []),
+         'effdet_launch_count': (ctypes.c_uint64, []), 'effdet_reset_launch_count': (None, [])}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load the shared object (no compute).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(SO_PATH):
+                raise EffdetNativeError(
+                    'effdet_b200: %s is missing - build it with `python __graft_entry__.py` '
+                    '(there is no CPU / PyTorch fallback for the hot path)' % SO_PATH)
+            lib = ctypes.CDLL(SO_PATH)
+            for name, argtypes in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argtypes
+                fn.restype = ctypes.c_int
+            for name, (res, argtypes) in PLAIN.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argtypes
+                fn.restype = res
+            _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().effdet_last_error().decode('utf-8', 'replace')
+
+
+def launch_count():
+    return int(load().effdet_launch_count())
+
+
+def reset_launch_count():
+    load().effdet_reset_launch_count()
+
+
+def ptr(t):
+    """Device pointer of a CUDA fp32 (or explicitly typed) tensor; None passes NULL."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EffdetNativeError('effdet_b200 kernels need CUDA tensors (got %s); there is no CPU path' % t.device)
+    return t.data_ptr()
+
+
+def f32(t, name='tensor'):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise EffdetNativeError('%s must be a CUDA float32 tensor (got %s on %s)' % (name, t.dtype, t.device))
+    if not t.is_contiguous():
+        raise EffdetNativeError('%s must be contiguous (shape %s strides %s)' % (name, tuple(t.shape), t.stride()))
+    return t.data_ptr()
+
+
+def call(name, dev_tensor, *args):
+    """Invoke an entry point on dev_tensor's device and the current stream of that device."""
+    lib = load()
+    dev = dev_tensor.device.index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = getattr(lib, name)(*args, dev, stream)
+    if rc != 0:
+        raise EffdetNativeError('%s failed (%d): %s' % (name, rc, last_error()))

@@ -1,0 +1,666 @@
+"""Host-side glue between the nn.Module mirror and the C ABI: tensor allocation, parameter-derived
+caches (packed weights, folded BatchNorm) and the ``torch.autograd.Function``s whose forward /
+backward are sequences of ``libeffdet_b200.so`` launches.  No arithmetic happens in PyTorch here
+(torch only allocates, zero-fills and takes views); gradients come back as ordinary ``.grad``
+so DDP's reducer hooks and ``clip_grad_norm_`` (reference train.py:114-116) keep working.
+
+Internal activation layout is NHWC fp32; module boundaries expose the same memory as a logical
+NCHW tensor with channels_last strides (zero-copy ``permute`` views).
+"""
+import weakref
+
+import torch
+
+from . import _native as N
+from ._native import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, FUSE_POOL, FUSE_UP
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers
+# ------------------------------------------------------------------------------------------------
+
+
+class _ToNHWC(torch.autograd.Function):
+    """NCHW-contiguous -> NHWC-contiguous through the library's tiled transpose."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        N.call('effdet_nchw_to_nhwc', x, N.f32(x, 'x'), N.f32(y), B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        B, H, W, C = dy.shape
+        dx = torch.empty((B, C, H, W), device=dy.device, dtype=torch.float32)
+        N.call('effdet_nhwc_to_nchw', dy, N.f32(dy), N.f32(dx), B, C, H, W)
+        return dx
+
+
+def check_cuda_f32(x, what):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise N.EffdetNativeError('%s: expected a CUDA tensor; the B200 hot path has no CPU fallback '
+                                  '(got %s)' % (what, getattr(x, 'device', type(x))))
+    if x.dtype != torch.float32:
+        raise N.EffdetNativeError('%s: expected float32, got %s' % (what, x.dtype))
+
+
+def to_nhwc(x, what='input'):
+    """Logical NCHW tensor -> NHWC-contiguous tensor (zero-copy when already channels_last)."""
+    check_cuda_f32(x, what)
+    if x.dim() != 4:
+        raise N.EffdetNativeError('%s: expected a 4-D NCHW tensor, got shape %s' % (what, tuple(x.shape)))
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    return _ToNHWC.apply(x)
+
+
+def to_nchw_view(y):
+    """NHWC-contiguous tensor -> logical NCHW view (channels_last strides, zero-copy)."""
+    return y.permute(0, 3, 1, 2)
+
+
+def _empty(shape, like):
+    return torch.empty(shape, device=like.device, dtype=torch.float32)
+
+
+def _zeros(shape, like):
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter-derived caches (invalidated by in-place updates: optimizer.step, load_state_dict)
+# ------------------------------------------------------------------------------------------------
+_cache = weakref.WeakKeyDictionary()
+
+
+def _cached(params, kind, builder):
+    key = params[0]
+    sig = tuple((p._version, p.data_ptr()) for p in params)
+    slot = _cache.get(key)
+    if slot is None:
+        slot = {}
+        _cache[key] = slot
+    hit = slot.get(kind)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    val = builder()
+    slot[kind] = (sig, val)
+    return val
+
+
+def pack_conv(w):
+    """OIHW parameter -> (forward pack [kk][Cin][Cout], dgrad pack [kk][Cout][Cin])."""
+    def build():
+        Cout, Cin, k, _ = w.shape
+        src = w.detach().contiguous()
+        wf = _empty((k * k, Cin, Cout), w)
+        wd = _empty((k * k, Cout, Cin), w)
+        N.call('effdet_pack_conv_weight', w, N.f32(src, 'conv weight'), N.f32(wf), N.f32(wd), Cout, Cin, k)
+        return wf, wd
+    return _cached([w], 'pack', build)
+
+
+def pack_dw(w):
+    """[C,1,k,k] depthwise parameter -> [k][k][C]."""
+    def build():
+        C, _, k, _ = w.shape
+        src = w.detach().contiguous()
+        o = _empty((k, k, C), w)
+        N.call('effdet_pack_dw_weight', w, N.f32(src, 'depthwise weight'), N.f32(o), C, k)
+        return o
+    return _cached([w], 'packdw', build)
+
+
+def bn_fold(gamma, beta, rmean, rvar, eps):
+    """Frozen BN -> (scale, shift, rstd), each [C]."""
+    def build():
+        C = gamma.numel()
+        scale, shift, rstd = _empty((C,), gamma), _empty((C,), gamma), _empty((C,), gamma)
+        N.call('effdet_bn_fold', gamma, N.f32(gamma.detach(), 'bn weight'), N.f32(beta.detach(), 'bn bias'),
+               N.f32(rmean, 'running_mean'), N.f32(rvar, 'running_var'), float(eps), N.f32(scale), N.f32(shift),
+               N.f32(rstd), C)
+        return scale, shift, rstd
+    return _cached([gamma, beta, rmean, rvar], 'fold', build)
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers over single entry points
+# ------------------------------------------------------------------------------------------------
+
+
+def conv2d_raw(dev_t, x_ptr, x_bs, wf, y_ptr, y_bs, B, H, W, Cin, Cout, k, z_ptr=None, bias=None, scale=None,
+               shift=None, a_scale=None, row_scale=None, res_ptr=None, res_bs=0, mask_ptr=None, mask_bs=0,
+               act=ACT_NONE):
+    a = N.ConvArgs(x_ptr, x_bs, N.f32(wf, 'packed weight'), y_ptr, y_bs, z_ptr, N.f32(bias, 'bias'),
+                   N.f32(scale, 'scale'), N.f32(shift, 'shift'), N.f32(a_scale, 'a_scale'),
+                   N.f32(row_scale, 'row_scale'), res_ptr, res_bs, mask_ptr, mask_bs, B, H, W, Cin, Cout, k, act)
+    N.call('effdet_conv2d', dev_t, a)
+
+
+def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_scale=None, residual=None,
+           mask_src=None, act=ACT_NONE, save_z=False):
+    """x NHWC contiguous -> y NHWC (and the raw pre-affine z when save_z)."""
+    B, H, W, Cin = x.shape
+    y = _empty((B, H, W, Cout), x)
+    z = _empty((B, H, W, Cout), x) if save_z else None
+    bs = H * W * Cout
+    conv2d_raw(x, N.f32(x, 'x'), H * W * Cin, wf, N.f32(y), bs, B, H, W, Cin, Cout, k, z_ptr=N.f32(z), bias=bias,
+               scale=scale, shift=shift, a_scale=a_scale, row_scale=row_scale, res_ptr=N.f32(residual, 'residual'),
+               res_bs=bs, mask_ptr=N.f32(mask_src, 'mask_src'), mask_bs=bs, act=act)
+    return (y, z) if save_z else y
+
+
+def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None):
+    a = N.WgradArgs(x_ptr, x_bs, dy_ptr, dy_bs, N.f32(dw, 'dw'), N.f32(dbias, 'dbias'), N.f32(a_scale, 'a_scale'),
+                    B, H, W, Cin, Cout, k)
+    N.call('effdet_conv2d_wgrad', dev_t, a)
+
+
+def conv_wgrad(x, dy, dw, dbias, k, a_scale=None):
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    conv_wgrad_raw(x, N.f32(x, 'x'), H * W * Cin, N.f32(dy, 'dy'), H * W * Cout, dw, dbias, B, H, W, Cin, Cout, k,
+                   a_scale=a_scale)
+
+
+def bnact_bwd(dy, z, scale, shift, mean, rstd, act, row_scale=None, gate=None, dmean=None):
+    """-> (dz, dgamma, dbeta) for y = act(z*scale+shift) [* row_scale]; SE mode when gate is given."""
+    B = z.shape[0]
+    C = z.shape[-1]
+    HW = z.numel() // (B * C)
+    dz = torch.empty_like(z)
+    dgamma, dbeta = _zeros((C,), z), _zeros((C,), z)
+    a = N.BnActBwdArgs(N.f32(dy, 'dy'), N.f32(z, 'z'), N.f32(dz), N.f32(scale), N.f32(shift), N.f32(mean, 'mean'),
+                       N.f32(rstd), N.f32(dgamma), N.f32(dbeta), N.f32(row_scale), N.f32(gate), N.f32(dmean),
+                       1.0 / HW, B, HW, C, act)
+    N.call('effdet_bnact_bwd', z, a)
+    return dz, dgamma, dbeta
+
+
+def add(a, b):
+    out = torch.empty_like(a)
+    N.call('effdet_add', a, N.f32(a, 'a'), N.f32(b, 'b'), N.f32(out), a.numel())
+    return out
+
+
+def _contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# Stem   (reference: models/efficientnet.py:193)
+# ------------------------------------------------------------------------------------------------
+
+
+class StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, rmean, rvar, eps):
+        check_cuda_f32(x, 'EfficientNet input')
+        x = _contig(x)
+        B, Cin, H, W = x.shape
+        if Cin != 3:
+            raise N.EffdetNativeError('stem expects 3 input channels, got %d' % Cin)
+        C0 = w.shape[0]
+        scale, shift, rstd = bn_fold(gamma, beta, rmean, rvar, eps)
+        Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+        z = _empty((B, Ho, Wo, C0), x)
+        y = _empty((B, Ho, Wo, C0), x)
+        wc = _contig(w.detach())
+        N.call('effdet_stem_fwd', x, N.f32(x, 'image'), N.f32(wc), N.f32(scale), N.f32(shift), N.f32(z), N.f32(y),
+               B, H, W, C0)
+        ctx.save_for_backward(x, z, scale, shift, rmean, rstd)
+        ctx.C0 = C0
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z, scale, shift, rmean, rstd = ctx.saved_tensors
+        dy = _contig(dy)
+        B, _, H, W = x.shape
+        dz, dgamma, dbeta = bnact_bwd(dy, z, scale, shift, rmean, rstd, ACT_SWISH)
+        dw = _zeros((ctx.C0, 3, 3, 3), x)
+        N.call('effdet_stem_wgrad', x, N.f32(x), N.f32(dz), N.f32(dw), B, H, W, ctx.C0)
+        return None, dw, dgamma, dbeta, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# MBConv block   (reference: models/efficientnet.py:75-105)
+# ------------------------------------------------------------------------------------------------
+
+
+class MBConvFn(torch.autograd.Function):
+    """args: x (NHWC), row_scale ([B] drop-connect multiplier or None), cfg dict, then parameters
+    [We,g0,b0,rm0,rv0]? Wd,g1,b1,rm1,rv1, Wr,br,Wx,bx, Wp,g2,b2,rm2,rv2."""
+
+    @staticmethod
+    def forward(ctx, x, row_scale, cfg, *P):
+        x = _contig(x)
+        B, H, W, Cin = x.shape
+        k, s, eps = cfg['k'], cfg['s'], cfg['eps']
+        i = 0
+        saved = {}
+        if cfg['expand']:
+            We, g0, b0, rm0, rv0 = P[0:5]
+            i = 5
+            sc0, sh0, rs0 = bn_fold(g0, b0, rm0, rv0, eps)
+            wf, _ = pack_conv(We)
+            a0, z0 = conv2d(x, wf, We.shape[0], 1, scale=sc0, shift=sh0, act=ACT_SWISH, save_z=True)
+            saved.update(z0=z0, sc0=sc0, sh0=sh0, rs0=rs0, rm0=rm0)
+        else:
+            a0 = x
+        Wd, g1, b1, rm1, rv1, Wr, br, Wx, bx, Wp, g2, b2, rm2, rv2 = P[i:i + 14]
+        C = Wd.shape[0]
+        sc1, sh1, rs1 = bn_fold(g1, b1, rm1, rv1, eps)
+        pt, pl = cfg['pad_t'], cfg['pad_l']
+        Ho = (H + cfg['pad_h'] - k) // s + 1
+        Wo = (W + cfg['pad_w'] - k) // s + 1
+        z1 = _empty((B, Ho, Wo, C), x)
+        a1 = _empty((B, Ho, Wo, C), x)
+        wkkc = pack_dw(Wd)
+        N.call('effdet_dwconv_fwd', x, N.f32(a0), N.f32(wkkc), N.f32(sc1), N.f32(sh1), N.f32(z1), N.f32(a1),
+               B, H, W, C, k, s, pt, pl, Ho, Wo)
+        # squeeze-excite
+        S = Wr.shape[0]
+        mean = _zeros((B, C), x)
+        N.call('effdet_spatial_reduce', x, N.f32(a1), None, N.f32(mean), 1.0 / (Ho * Wo), B, Ho * Wo, C)
+        s_pre = _empty((B, S), x)
+        gate = _empty((B, C), x)
+        wr, wx = _contig(Wr.detach()), _contig(Wx.detach())
+        N.call('effdet_se_gate_fwd', x, N.f32(mean), N.f32(wr), N.f32(br.detach()), N.f32(wx), N.f32(bx.detach()),
+               N.f32(s_pre), N.f32(gate), B, C, S)
+        # project (+BN, drop-connect, skip)
+        sc2, sh2, rs2 = bn_fold(g2, b2, rm2, rv2, eps)
+        wpf, _ = pack_conv(Wp)
+        Cout = Wp.shape[0]
+        skip = cfg['skip']
+        y, z2 = conv2d(a1, wpf, Cout, 1, scale=sc2, shift=sh2, a_scale=gate,
+                       row_scale=row_scale if skip else None, residual=x if skip else None, save_z=True)
+        ctx.cfg = cfg
+        ctx.P = P
+        ctx.t = dict(saved, x=x, a0=a0, z1=z1, a1=a1, mean=mean, s_pre=s_pre, gate=gate, z2=z2, sc1=sc1, sh1=sh1,
+                     rs1=rs1, rm1=rm1, sc2=sc2, sh2=sh2, rs2=rs2, rm2=rm2, row_scale=row_scale if skip else None,
+                     wkkc=wkkc, dims=(B, H, W, Ho, Wo))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cfg, P, t = ctx.cfg, ctx.P, ctx.t
+        dy = _contig(dy)
+        x = t['x']
+        B, H, W, Ho, Wo = t['dims']
+        k, s = cfg['k'], cfg['s']
+        i = 5 if cfg['expand'] else 0
+        Wd, g1, b1, rm1, rv1, Wr, br, Wx, bx, Wp, g2, b2, rm2, rv2 = P[i:i + 14]
+        C = Wd.shape[0]
+        a1, gate = t['a1'], t['gate']
+        # project BN (no activation), drop-connect scale folded in
+        dz2, dg2, db2 = bnact_bwd(dy, t['z2'], t['sc2'], t['sh2'], t['rm2'], t['rs2'], ACT_NONE,
+                                  row_scale=t['row_scale'])
+        dWp = torch.zeros_like(Wp)
+        conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate)
+        _, wpd = pack_conv(Wp)
+        dq = conv2d(dz2, wpd, C, 1)                      # grad w.r.t. (a1 * gate)
+        # squeeze-excite backward
+        dgate = _zeros((B, C), x)
+        N.call('effdet_spatial_reduce', x, N.f32(dq), N.f32(a1), N.f32(dgate), 1.0, B, Ho * Wo, C)
+        S = Wr.shape[0]
+        dmean = _empty((B, C), x)
+        dWr, dbr, dWx, dbx = torch.zeros_like(Wr), torch.zeros_like(br), torch.zeros_like(Wx), torch.zeros_like(bx)
+        N.call('effdet_se_gate_bwd', x, N.f32(dgate), N.f32(t['mean']), N.f32(t['s_pre']), N.f32(gate),
+               N.f32(_contig(Wr.detach())), N.f32(_contig(Wx.detach())), N.f32(dmean), N.f32(dWr), N.f32(dbr),
+               N.f32(dWx), N.f32(dbx), B, C, S)
+        # depthwise BN+swish backward with the SE product rule fused in
+        dz1, dg1, db1 = bnact_bwd(dq, t['z1'], t['sc1'], t['sh1'], t['rm1'], t['rs1'], ACT_SWISH, gate=gate,
+                                  dmean=dmean)
+        a0 = t['a0']
+        dWd = torch.zeros_like(Wd)
+        N.call('effdet_dwconv_bwd_weight', x, N.f32(a0), N.f32(dz1), N.f32(dWd), B, H, W, C, k, s, cfg['pad_t'],
+               cfg['pad_l'], Ho, Wo)
+        da0 = _empty((B, H, W, C), x)
+        N.call('effdet_dwconv_bwd_data', x, N.f32(dz1), N.f32(t['wkkc']), N.f32(da0), B, H, W, C, k, s,
+               cfg['pad_t'], cfg['pad_l'], Ho, Wo)
+        grads = []
+        if cfg['expand']:
+            We = P[0]
+            dz0, dg0, db0 = bnact_bwd(da0, t['z0'], t['sc0'], t['sh0'], t['rm0'], t['rs0'], ACT_SWISH)
+            dWe = torch.zeros_like(We)
+            conv_wgrad(x, dz0, dWe, None, 1)
+            _, wed = pack_conv(We)
+            dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None)
+            grads += [dWe, dg0, db0, None, None]
+        else:
+            dx = add(da0, dy) if cfg['skip'] else da0
+        grads += [dWd, dg1, db1, None, None, dWr, dbr, dWx, dbx, dWp, dg2, db2, None, None]
+        ctx.t = None
+        return (dx, None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# Generic ConvModule: conv + bias (+ReLU)   (reference: models/module.py:507-515)
+# ------------------------------------------------------------------------------------------------
+
+
+class ConvBiasActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        x = _contig(x)
+        k = w.shape[2]
+        wf, _ = pack_conv(w)
+        y = conv2d(x, wf, w.shape[0], k, bias=b.detach() if b is not None else None, act=act)
+        ctx.save_for_backward(x, y if act == ACT_RELU else None)
+        ctx.w, ctx.b, ctx.act = w, b, act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        dy = _contig(dy)
+        if ctx.act == ACT_RELU:
+            dz = torch.empty_like(dy)
+            N.call('effdet_relu_bwd', dy, N.f32(dy), N.f32(y), N.f32(dz), dy.numel())
+        else:
+            dz = dy
+        k = w.shape[2]
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(b) if b is not None else None
+        conv_wgrad(x, dz, dw, db, k)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, wd = pack_conv(w)
+            dx = conv2d(dz, wd, x.shape[3], k)
+        return dx, dw, db, None
+
+
+# ------------------------------------------------------------------------------------------------
+# One BiFPN layer   (reference: BiFPNModule.forward, models/bifpn.py:172-203)
+# ------------------------------------------------------------------------------------------------
+
+
+def _fuse_fwd(a, b, c, w, col, eps, mode):
+    B, H, W, C = a.shape
+    out = torch.empty_like(a)
+    wst = w.shape[1]
+    args = N.FuseArgs(N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(out), B, H, W, C, mode)
+    N.call('effdet_bifpn_fuse_fwd', a, args)
+    return out
+
+
+def _fuse_bwd(dout, a, b, c, w, col, eps, mode, da, acc_a, db, acc_b, dc, acc_c, dw):
+    B, H, W, C = a.shape
+    scratch = _zeros((4,), a)
+    wst = w.shape[1]
+    args = N.FuseBwdArgs(N.f32(dout), N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(da),
+                         N.f32(db), N.f32(dc), acc_a, acc_b, acc_c, dw.data_ptr() + 4 * col, N.f32(scratch),
+                         B, H, W, C, mode)
+    N.call('effdet_bifpn_fuse_bwd', a, args)
+
+
+class BiFPNLayerFn(torch.autograd.Function):
+    """args: eps, L, in[0..L-1] (NHWC, fine->coarse), w1 [2,L], w2 [3,L-2], then (weight, bias) x 2(L-1)."""
+
+    @staticmethod
+    def forward(ctx, eps, L, *args):
+        ins = [_contig(t) for t in args[:L]]
+        w1, w2 = args[L], args[L + 1]
+        convs = args[L + 2:]
+        w1c, w2c = _contig(w1.detach()), _contig(w2.detach())
+        C = ins[0].shape[3]
+
+        def conv(idx, f):
+            wf, _ = pack_conv(convs[2 * idx])
+            return conv2d(f, wf, C, 3, bias=convs[2 * idx + 1].detach())
+
+        fused = [None] * (2 * (L - 1))
+        td = [None] * L
+        td[L - 1] = ins[L - 1]
+        idx = 0
+        for i in range(L - 1, 0, -1):                       # top-down
+            f = _fuse_fwd(ins[i - 1], td[i], None, w1c, i - 1, eps, FUSE_UP)
+            fused[idx] = f
+            td[i - 1] = conv(idx, f)
+            idx += 1
+        out = [None] * L
+        out[0] = td[0]
+        for i in range(0, L - 2):                           # bottom-up
+            f = _fuse_fwd(td[i + 1], out[i], ins[i + 1], w2c, i, eps, FUSE_POOL)
+            fused[idx] = f
+            out[i + 1] = conv(idx, f)
+            idx += 1
+        f = _fuse_fwd(ins[L - 1], out[L - 2], None, w1c, L - 1, eps, FUSE_POOL)   # top level
+        fused[idx] = f
+        out[L - 1] = conv(idx, f)
+        ctx.eps, ctx.L = eps, L
+        ctx.keep = (ins, td, out, fused, w1, w2, w1c, w2c, convs)
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        eps, L = ctx.eps, ctx.L
+        ins, td, out, fused, w1, w2, w1c, w2c, convs = ctx.keep
+        douts = [_contig(d) for d in douts]
+        C = ins[0].shape[3]
+        dw1, dw2 = torch.zeros_like(w1c), torch.zeros_like(w2c)
+        dconv = [None] * len(convs)
+
+        def conv_bwd(idx, dy):
+            w, b = convs[2 * idx], convs[2 * idx + 1]
+            dw, db = torch.zeros_like(w), torch.zeros_like(b)
+            conv_wgrad(fused[idx], dy, dw, db, 3)
+            dconv[2 * idx], dconv[2 * idx + 1] = dw, db
+            _, wd = pack_conv(w)
+            return conv2d(dy, wd, C, 3)
+
+        g_in = [None] * L
+        g_td = [None] * L
+        g_out = [None] * L
+        # top level: out[L-1] = conv_last(fuse_pool(in[L-1], out[L-2]))
+        idx = 2 * (L - 1) - 1
+        df = conv_bwd(idx, douts[L - 1])
+        g_in[L - 1] = torch.empty_like(ins[L - 1])
+        buf = torch.empty_like(out[L - 2])
+        _fuse_bwd(df, ins[L - 1], out[L - 2], None, w1c, L - 1, eps, FUSE_POOL, g_in[L - 1], 0, buf, 0, None, 0, dw1)
+        g_out[L - 2] = add(douts[L - 2], buf)
+        # bottom-up nodes in reverse
+        for i in range(L - 3, -1, -1):
+            idx -= 1
+            df = conv_bwd(idx, g_out[i + 1])
+            g_td[i + 1] = torch.empty_like(td[i + 1])
+            g_in[i + 1] = torch.empty_like(ins[i + 1])
+            buf = torch.empty_like(out[i])
+            _fuse_bwd(df, td[i + 1], out[i], ins[i + 1], w2c, i, eps, FUSE_POOL, g_td[i + 1], 0, buf, 0,
+                      g_in[i + 1], 0, dw2)
+            g = add(douts[i], buf)
+            if i == 0:
+                g_td[0] = g                                  # out[0] is td[0]
+            else:
+                g_out[i] = g
+        # top-down nodes in reverse of their forward order
+        for i in range(1, L):
+            idx = L - 1 - i
+            df = conv_bwd(idx, g_td[i - 1])
+            if i - 1 == 0:
+                g_in[0] = torch.empty_like(ins[0])
+                acc_a = 0
+            else:
+                acc_a = 1
+            db_t = g_in[L - 1] if i == L - 1 else g_td[i]
+            _fuse_bwd(df, ins[i - 1], td[i], None, w1c, i - 1, eps, FUSE_UP, g_in[i - 1], acc_a, db_t, 1, None, 0, dw1)
+        ctx.keep = None
+        return (None, None) + tuple(g_in) + (dw1, dw2) + tuple(dconv)
+
+
+# ------------------------------------------------------------------------------------------------
+# RetinaHead over all pyramid levels   (reference: models/retinahead.py:109-132)
+# ------------------------------------------------------------------------------------------------
+
+
+class RetinaHeadFn(torch.autograd.Function):
+    """args: nlevels, num_anchors, num_classes, stacked, feats..., then parameters in the order
+    cls_convs (w,b)*stacked, reg_convs (w,b)*stacked, retina_cls w,b, retina_reg w,b.
+    Returns (cls [B, sum(HWA), K] after sigmoid, reg [B, sum(HWA), 4]) -- already concatenated."""
+
+    @staticmethod
+    def forward(ctx, nl, A, K, stacked, *args):
+        feats = [_contig(t) for t in args[:nl]]
+        P = args[nl:]
+        cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
+        wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
+        B = feats[0].shape[0]
+        F = cls_p[0].shape[0]
+        offs, tot = [], 0
+        for f in feats:
+            offs.append(tot)
+            tot += f.shape[1] * f.shape[2] * A
+        cls_all = _empty((B, tot, K), feats[0])
+        reg_all = _empty((B, tot, 4), feats[0])
+        acts = []
+        wcf, _ = pack_conv(wc)
+        wrf, _ = pack_conv(wr)
+        for lv, f in enumerate(feats):
+            _, H, W, Cin = f.shape
+            c, r = f, f
+            ca, ra = [f], [f]
+            for i in range(stacked):
+                wf, _ = pack_conv(cls_p[2 * i])
+                c = conv2d(c, wf, F, 3, bias=cls_p[2 * i + 1].detach(), act=ACT_RELU)
+                ca.append(c)
+            for i in range(stacked):
+                wf, _ = pack_conv(reg_p[2 * i])
+                r = conv2d(r, wf, F, 3, bias=reg_p[2 * i + 1].detach(), act=ACT_RELU)
+                ra.append(r)
+            conv2d_raw(f, N.f32(c), H * W * F, wcf, cls_all.data_ptr() + 4 * offs[lv] * K, tot * K, B, H, W, F,
+                       A * K, 3, bias=bc.detach(), act=ACT_SIGMOID)
+            conv2d_raw(f, N.f32(r), H * W * F, wrf, reg_all.data_ptr() + 4 * offs[lv] * 4, tot * 4, B, H, W, F,
+                       A * 4, 3, bias=br.detach())
+            acts.append((ca, ra))
+        ctx.meta = (nl, A, K, stacked, offs, tot)
+        ctx.keep = (feats, P, acts, cls_all)
+        return cls_all, reg_all
+
+    @staticmethod
+    def backward(ctx, dcls, dreg):
+        nl, A, K, stacked, offs, tot = ctx.meta
+        feats, P, acts, cls_all = ctx.keep
+        cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
+        wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
+        B = feats[0].shape[0]
+        F = cls_p[0].shape[0]
+        dcls, dreg = _contig(dcls), _contig(dreg)
+        dzc = torch.empty_like(dcls)
+        N.call('effdet_sigmoid_bwd', dcls, N.f32(dcls), N.f32(cls_all), N.f32(dzc), dcls.numel())
+        gP = [torch.zeros_like(p) for p in P]
+        g_cls, g_reg = gP[:2 * stacked], gP[2 * stacked:4 * stacked]
+        gwc, gbc, gwr, gbr = gP[4 * stacked:4 * stacked + 4]
+        _, wcd = pack_conv(wc)
+        _, wrd = pack_conv(wr)
+        dfeats = []
+        for lv, f in enumerate(feats):
+            _, H, W, Cin = f.shape
+            ca, ra = acts[lv]
+            outs = []
+            for (tower, tp, tg, wl, gwl, gbl, wld, dptr, width) in (
+                    (ca, cls_p, g_cls, wc, gwc, gbc, wcd, dzc.data_ptr() + 4 * offs[lv] * K, K),
+                    (ra, reg_p, g_reg, wr, gwr, gbr, wrd, dreg.data_ptr() + 4 * offs[lv] * 4, 4)):
+                top = tower[stacked]
+                Co = A * width
+                conv_wgrad_raw(f, N.f32(top), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3)
+                d = _empty((B, H, W, F), f)
+                bs = H * W * F
+                conv2d_raw(f, dptr, tot * width, wld, N.f32(d), bs, B, H, W, Co, F, 3, mask_ptr=N.f32(top), mask_bs=bs)
+                for i in range(stacked - 1, -1, -1):
+                    xin = tower[i]
+                    conv_wgrad(xin, d, tg[2 * i], tg[2 * i + 1], 3)
+                    _, wd = pack_conv(tp[2 * i])
+                    if i > 0:
+                        d = conv2d(d, wd, F, 3, mask_src=xin)
+                    else:
+                        d = conv2d(d, wd, Cin, 3, residual=outs[0] if outs else None)
+                outs.append(d)
+            dfeats.append(outs[-1])
+        ctx.keep = None
+        return (None, None, None, None) + tuple(dfeats) + tuple(gP)
+
+
+# ------------------------------------------------------------------------------------------------
+# FocalLoss   (reference: models/losses.py:32-152)
+# ------------------------------------------------------------------------------------------------
+
+
+class FocalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cls, reg, anchors, annots, alpha, gamma):
+        check_cuda_f32(cls, 'classifications')
+        check_cuda_f32(reg, 'regressions')
+        cls, reg = _contig(cls), _contig(reg)
+        anchors = _contig(anchors.to(device=cls.device, dtype=torch.float32))
+        annots = _contig(annots.to(device=cls.device, dtype=torch.float32))
+        B, A, K = cls.shape
+        G = annots.shape[1]
+        losses = _empty((2,), cls)
+        assign = torch.empty((B, A), device=cls.device, dtype=torch.int32)
+        stats = _empty((B, 4), cls)
+        N.call('effdet_focal_loss_fwd', cls, N.f32(cls), N.f32(reg), N.f32(anchors.view(-1, 4)), N.f32(annots),
+               N.f32(losses), assign.data_ptr(), N.f32(stats), B, A, K, G, float(alpha), float(gamma))
+        ctx.save_for_backward(cls, reg, anchors, annots, assign, stats)
+        ctx.hp = (float(alpha), float(gamma))
+        return losses.narrow(0, 0, 1), losses.narrow(0, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        cls, reg, anchors, annots, assign, stats = ctx.saved_tensors
+        B, A, K = cls.shape
+        G = annots.shape[1]
+        gout = _zeros((2,), cls)
+        if g_cls is not None:
+            gout[0:1].copy_(g_cls.reshape(1))
+        if g_reg is not None:
+            gout[1:2].copy_(g_reg.reshape(1))
+        dcls, dreg = torch.empty_like(cls), torch.empty_like(reg)
+        N.call('effdet_focal_loss_bwd', cls, N.f32(cls), N.f32(reg), N.f32(anchors.view(-1, 4)), N.f32(annots),
+               N.f32(gout), assign.data_ptr(), N.f32(stats), N.f32(dcls), N.f32(dreg), B, A, K, G, ctx.hp[0], ctx.hp[1])
+        return dcls, dreg, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# Inference post-processing   (reference: models/efficientdet.py:70-86)
+# ------------------------------------------------------------------------------------------------
+
+
+def detect_image0(cls, reg, anchors, img_h, img_w, threshold, iou_threshold):
+    """-> [scores[K], classes[K] int64, boxes[K,4]] for image 0, or None when nothing passes."""
+    cls0, reg0 = _contig(cls[0]), _contig(reg[0])
+    A, K = cls0.shape
+    anchors = _contig(anchors.view(-1, 4))
+    npad = 1
+    while npad < A:
+        npad *= 2
+    dev = cls0.device
+    boxes = _empty((A, 4), cls0)
+    scores = _empty((A,), cls0)
+    classes = torch.empty((A,), device=dev, dtype=torch.int32)
+    keys = torch.empty((npad,), device=dev, dtype=torch.int64)
+    count = torch.empty((1,), device=dev, dtype=torch.int32)
+    N.call('effdet_detect_candidates', cls0, N.f32(cls0), N.f32(reg0), N.f32(anchors), N.f32(boxes), N.f32(scores),
+           classes.data_ptr(), keys.data_ptr(), count.data_ptr(), A, K, npad, float(img_w), float(img_h),
+           float(threshold))
+    n = int(count.item())                       # host reads one int to size the NMS workspace
+    if n == 0:
+        return None
+    cb = (n + 63) // 64
+    mask = torch.empty((n * cb,), device=dev, dtype=torch.int64)
+    keep = torch.empty((n,), device=dev, dtype=torch.int32)
+    nkeep = torch.empty((1,), device=dev, dtype=torch.int32)
+    N.call('effdet_nms', cls0, N.f32(boxes), keys.data_ptr(), n, float(iou_threshold), mask.data_ptr(),
+           keep.data_ptr(), nkeep.data_ptr())
+    m = int(nkeep.item())
+    o_s = _empty((m,), cls0)
+    o_c = torch.empty((m,), device=dev, dtype=torch.int64)
+    o_b = _empty((m, 4), cls0)
+    N.call('effdet_gather_detections', cls0, N.f32(boxes), N.f32(scores), classes.data_ptr(), keep.data_ptr(), m,
+           N.f32(o_s), o_c.data_ptr(), N.f32(o_b))
+    return [o_s, o_c, o_b]

@@ -1,0 +1,237 @@
+/* effdet_b200 -- C ABI of the B200-native (sm_100a) EfficientDet forward/backward hot path.
+ *
+ * The reference (toandaominh1997/EfficientDet.Pytorch @ fbe56e5) is 100% Python and has NO
+ * native boundary of its own: every entry point below replaces a chain of ATen/cuDNN/torchvision
+ * calls made by the cited reference lines.  The reference-side binding is the ctypes stub in
+ * INTEGRATION.md (a Python reference binds through ctypes/`torch.autograd.Function`).
+ *
+ * Conventions
+ *   - all tensors are fp32, dense, NHWC ("[B,H,W,C]") unless a comment says otherwise;
+ *     pointers are device pointers owned by the caller (PyTorch's caching allocator);
+ *   - nothing here allocates, frees, retains a pointer after return, or synchronises the device;
+ *   - every call takes the CUDA device ordinal and the cudaStream_t to launch on;
+ *   - return value 0 = launched; negative = error, text via effdet_last_error() (thread-local);
+ *   - "+=" in a comment means the kernel ACCUMULATES into a caller-initialised buffer.
+ */
+#ifndef EFFDET_B200_H
+#define EFFDET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFFDET_OK 0
+#define EFFDET_ERR_ARG (-1)
+#define EFFDET_ERR_LAUNCH (-2)
+#define EFFDET_ERR_DEVICE (-3)
+#define EFFDET_ERR_UNSUPPORTED (-4)
+
+#define EFFDET_ACT_NONE 0
+#define EFFDET_ACT_RELU 1
+#define EFFDET_ACT_SWISH 2
+#define EFFDET_ACT_SIGMOID 3
+
+#define EFFDET_FUSE_UP 0   /* second input is the coarser map, nearest x2 (models/bifpn.py:189) */
+#define EFFDET_FUSE_POOL 1 /* second input is the finer map, 2x2/2 max-pool (models/bifpn.py:195,200) */
+
+typedef void* effdet_stream_t; /* cudaStream_t */
+
+int effdet_version(void);
+const char* effdet_last_error(void);
+uint64_t effdet_launch_count(void); /* kernels launched by this library in this process */
+void effdet_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense convolution, k in {1,3}, stride 1, "same" zero padding, as an implicit GEMM
+ *   y[b,p,n] = epilogue( sum_{tap,c} x[b, p+tap, c] * a_scale[b,c] * w[tap,c,n] )
+ * Replaces F.conv2d + bias + BatchNorm(eval) + activation + residual in
+ *   ConvModule.forward           models/module.py:507-515   (neck 1x1/3x3, head 3x3 + ReLU)
+ *   RetinaHead.forward_single    models/retinahead.py:109-129 (retina_cls + sigmoid, retina_reg)
+ *   MBConvBlock.forward          models/efficientnet.py:85,96-104 (expand / project 1x1)
+ * and, with the flipped/transposed weight pack, the data gradient of each of them.
+ * Epilogue order: v = acc + bias;  z = v (optional save);  v = v*scale + shift;  v = act(v);
+ *                 v *= row_scale[b];  v += residual;  v = mask_src > 0 ? v : 0;  y = v.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* x;        int64_t x_bstride; /* [B,H,W,Cin]; elements between consecutive images */
+    const float* w;                            /* packed [k*k][Cin][Cout] (effdet_pack_conv_weight) */
+    float* y;              int64_t y_bstride; /* [B,H,W,Cout]; stride lets the head write straight
+                                                  into the concatenated [B, sum(HWA), K] buffer
+                                                  (kills torch.cat, models/efficientdet.py:64-65) */
+    float* z;                                  /* optional raw (pre-affine) output, y's layout */
+    const float* bias;                         /* [Cout] or NULL */
+    const float* scale;    const float* shift; /* [Cout] eval-BN affine, or both NULL */
+    const float* a_scale;                      /* [B,Cin] squeeze-excite gate on the input, or NULL */
+    const float* row_scale;                    /* [B] drop-connect keep/keep_prob, or NULL */
+    const float* residual; int64_t r_bstride;  /* [B,H,W,Cout] added last, or NULL */
+    const float* mask_src; int64_t m_bstride;  /* [B,H,W,Cout]: ReLU-backward mask source, or NULL */
+    int32_t B, H, W, Cin, Cout, ksize, act;
+} effdet_conv_args;
+int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream);
+
+/* Weight gradient (and optional bias gradient) of the convolution above.
+ *   dw[n,c,ky,kx] += sum_{b,p} x[b,p+tap,c]*a_scale[b,c] * dy[b,p,n]     (OIHW, as .grad)
+ *   dbias[n]      += sum_{b,p} dy[b,p,n]
+ * Replaces cuDNN bwd-filter reached through autograd. */
+typedef struct {
+    const float* x;   int64_t x_bstride;
+    const float* dy;  int64_t dy_bstride;
+    float* dw;        /* [Cout,Cin,k,k]  += */
+    float* dbias;     /* [Cout] += , or NULL */
+    const float* a_scale;
+    int32_t B, H, W, Cin, Cout, ksize;
+} effdet_wgrad_args;
+int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
+
+/* OIHW -> [k*k][Cin][Cout] (forward) and, if w_dgrad != NULL, the 180-degree-rotated transpose
+ * [k*k][Cout][Cin] that turns the data gradient into the same implicit GEMM. */
+int effdet_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int ksize,
+                            int device, effdet_stream_t stream);
+
+/* out[n] += sum_m x[m,n]   (bias gradients, BN beta gradients) */
+int effdet_colsum(const float* x, float* out, int64_t M, int N, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stem: 3x3 stride-2 conv on the NCHW image with TF-"SAME" pad (0,1,0,1), eval-BN, swish.
+ * Replaces EfficientNet.extract_features stem, models/efficientnet.py:193 (+ utils.py:126-155).
+ *   x [B,3,H,W] NCHW  ->  z (raw conv) and y = swish(z*scale+shift), both [B,H/2,W/2,C0] NHWC
+ * ------------------------------------------------------------------------------------------ */
+int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float* z,
+                    float* y, int B, int H, int W, int C0, int device, effdet_stream_t stream);
+/* dw[C0,3,3,3] += sum x * dz   (the image needs no data gradient) */
+int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw_oihw, int B, int H, int W, int C0,
+                      int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Depthwise k x k (k in {3,5}), stride in {1,2}, asymmetric TF-"SAME" pad, eval-BN, swish.
+ * Replaces MBConvBlock.forward depthwise phase, models/efficientnet.py:87.
+ *   x [B,H,W,C] -> z raw, y = swish(z*scale+shift), both [B,Ho,Wo,C];  w_kkc = [k][k][C]
+ * ------------------------------------------------------------------------------------------ */
+int effdet_dwconv_fwd(const float* x, const float* w_kkc, const float* scale, const float* shift, float* z, float* y,
+                      int B, int H, int W, int C, int k, int stride, int pad_t, int pad_l, int Ho, int Wo,
+                      int device, effdet_stream_t stream);
+int effdet_dwconv_bwd_data(const float* dz, const float* w_kkc, float* dx, int B, int H, int W, int C, int k,
+                           int stride, int pad_t, int pad_l, int Ho, int Wo, int device, effdet_stream_t stream);
+/* dw[C,1,k,k] += ... */
+int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* dw_c1kk, int B, int H, int W, int C, int k,
+                             int stride, int pad_t, int pad_l, int Ho, int Wo, int device, effdet_stream_t stream);
+int effdet_pack_dw_weight(const float* w_c1kk, float* w_kkc, int C, int k, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of  y = act(BN_eval(z)) [* row_scale]  with frozen statistics but trainable affine
+ * (models/efficientdet.py:88-92; swish backward models/utils.py:38-42):
+ *   g  = dy*row_scale[b]            (or, SE mode:  g = dy*gate[b,c] + dmean[b,c]*inv_hw)
+ *   du = g * act'(z*scale+shift);  dgamma += sum du*(z-mean)*rstd;  dbeta += sum du;  dz = du*scale
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* dy;    /* [B,HW,C] */
+    const float* z;     /* [B,HW,C] raw conv output */
+    float* dz;          /* [B,HW,C] */
+    const float* scale; const float* shift; const float* mean; const float* rstd; /* [C] */
+    float* dgamma;      float* dbeta;   /* [C] += */
+    const float* row_scale; /* [B] or NULL */
+    const float* gate;      /* [B,C] or NULL */
+    const float* dmean;     /* [B,C] or NULL */
+    float inv_hw;
+    int32_t B, HW, C, act;  /* act: EFFDET_ACT_NONE or EFFDET_ACT_SWISH */
+} effdet_bnact_bwd_args;
+int effdet_bnact_bwd(const effdet_bnact_bwd_args* a, int device, effdet_stream_t stream);
+
+/* Frozen BatchNorm2d (eval mode even while training, models/efficientdet.py:88-92) folded to a
+ * per-channel affine: rstd = 1/sqrt(var+eps), scale = gamma*rstd, shift = beta - mean*scale. */
+int effdet_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* scale,
+                   float* shift, float* rstd, int C, int device, effdet_stream_t stream);
+/* out = a + b (skip-connection gradient join) ;  dz = y > 0 ? dy : 0 (stand-alone ReLU backward) */
+int effdet_add(const float* a, const float* b, float* out, int64_t n, int device, effdet_stream_t stream);
+int effdet_relu_bwd(const float* dy, const float* y, float* dz, int64_t n, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Squeeze-excite (models/efficientnet.py:90-94).
+ *   effdet_spatial_reduce : out[b,c] += alpha * sum_hw a[b,hw,c] * (b2 ? b2[b,hw,c] : 1)
+ *   effdet_se_gate_fwd    : s_pre = W1*mean+b1 ; gate = sigmoid(W2*swish(s_pre)+b2)
+ *   effdet_se_gate_bwd    : given dgate -> dmean, and += into dW1,db1,dW2,db2
+ * W1 = _se_reduce.weight [S,C], W2 = _se_expand.weight [C,S].
+ * ------------------------------------------------------------------------------------------ */
+int effdet_spatial_reduce(const float* a, const float* b2, float* out, float alpha, int B, int HW, int C,
+                          int device, effdet_stream_t stream);
+int effdet_se_gate_fwd(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
+                       float* s_pre, float* gate, int B, int C, int S, int device, effdet_stream_t stream);
+int effdet_se_gate_bwd(const float* dgate, const float* mean, const float* s_pre, const float* gate,
+                       const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2,
+                       float* db2, int B, int C, int S, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BiFPN fast-normalised fusion node input (BiFPNModule.forward, models/bifpn.py:177-201):
+ *   r = relu(w_col); n = r/(sum r + eps); out = sum_j n_j*in_j / (sum_j n_j + eps)
+ *   in_0 = a; in_1 = up2(b) or maxpool2(b); in_2 = c (3-input nodes only)
+ * The raw weight column is read as w[j*w_stride], j < (c ? 3 : 2).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* a; const float* b; const float* c;
+    const float* w; int32_t w_stride; float eps;
+    float* out;
+    int32_t B, H, W, C, mode; /* H,W = resolution of a/out */
+} effdet_fuse_args;
+int effdet_bifpn_fuse_fwd(const effdet_fuse_args* a, int device, effdet_stream_t stream);
+
+typedef struct {
+    const float* dout;
+    const float* a; const float* b; const float* c;
+    const float* w; int32_t w_stride; float eps;
+    float* da; float* db; float* dc;  /* input gradients (dc NULL for 2-input nodes) */
+    int32_t acc_a, acc_b, acc_c;      /* 0: overwrite, 1: += */
+    float* dw;                        /* gradient of the raw weights, indexed like w, += */
+    float* scratch;                   /* [4] floats, zero on entry */
+    int32_t B, H, W, C, mode;
+} effdet_fuse_bwd_args;
+int effdet_bifpn_fuse_bwd(const effdet_fuse_bwd_args* a, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FocalLoss.forward (models/losses.py:32-152): IoU assignment + focal BCE + smooth-L1, no host
+ * sync, no per-image Python loop.
+ *   cls [B,A,K] probabilities, reg [B,A,4], anchors [A,4] (x1,y1,x2,y2), annots [B,G,5] (-1 pad)
+ *   fwd: losses[0] = mean_b cls_loss_b, losses[1] = mean_b reg_loss_b;
+ *        assign_ws [B,A] int32 (>=0 matched annotation row, -1 background, -2 ignored, -3 image
+ *        without boxes) and stats_ws [B,4] float (npos, cls_sum, reg_sum, -) are kept for bwd.
+ *   bwd: dcls = gout[0] * d losses[0]/d cls ; dreg = gout[1] * d losses[1]/d reg
+ *        (gout: the two upstream gradients, read from DEVICE memory -> no sync).
+ * ------------------------------------------------------------------------------------------ */
+int effdet_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* annots,
+                          float* losses, int32_t* assign_ws, float* stats_ws, int B, int A, int K, int G,
+                          float alpha, float gamma, int device, effdet_stream_t stream);
+int effdet_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* annots,
+                          const float* gout, const int32_t* assign_ws, const float* stats_ws, float* dcls,
+                          float* dreg, int B, int A, int K, int G, float alpha, float gamma, int device,
+                          effdet_stream_t stream);
+/* y = g * p*(1-p) (sigmoid backward) ; y may alias g */
+int effdet_sigmoid_bwd(const float* g, const float* p, float* y, int64_t n, int device, effdet_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * Inference post-processing of image 0 (models/efficientdet.py:70-86, models/module.py:24-67,
+ * torchvision.ops.nms): decode + clip + class max + threshold + sort + greedy NMS, all on the
+ * device; the host only reads the two counters to size its output tensors.
+ * ------------------------------------------------------------------------------------------ */
+/* boxes[A,4], scores[A], classes[A]; keys[npad] (npad = pow2 >= A) sorted ascending so that
+ * entry j < *count is the j-th best candidate (score desc, anchor index asc); count[0] = #cands. */
+int effdet_detect_candidates(const float* cls, const float* reg, const float* anchors, float* boxes, float* scores,
+                             int32_t* classes, uint64_t* keys, int32_t* count, int A, int K, int npad,
+                             float img_w, float img_h, float threshold, int device, effdet_stream_t stream);
+/* mask_ws: n * ceil(n/64) uint64; keep_idx[n] int32 (anchor indices, best first); nkeep[0] */
+int effdet_nms(const float* boxes, const uint64_t* keys, int n, double iou_threshold, uint64_t* mask_ws,
+               int32_t* keep_idx, int32_t* nkeep, int device, effdet_stream_t stream);
+/* gathers scores/classes(int64)/boxes rows listed in keep_idx */
+int effdet_gather_detections(const float* boxes, const float* scores, const int32_t* classes,
+                             const int32_t* keep_idx, int nkeep, float* out_scores, int64_t* out_classes,
+                             float* out_boxes, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout plumbing at the module boundary (callers see logical NCHW, kernels are NHWC).
+ * ------------------------------------------------------------------------------------------ */
+int effdet_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, int device, effdet_stream_t stream);
+int effdet_nhwc_to_nchw(const float* x, float* y, int B, int C, int H, int W, int device, effdet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFDET_B200_H */
