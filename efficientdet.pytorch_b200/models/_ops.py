@@ -74,21 +74,22 @@ def _zeros(shape, like):
 # ------------------------------------------------------------------------------------------------
 # parameter-derived caches (invalidated by in-place updates: optimizer.step, load_state_dict)
 # ------------------------------------------------------------------------------------------------
-_cache = weakref.WeakKeyDictionary()
+_cache = {}   # id(first tensor) -> (weakref to it, {kind: (signature, value)})
 
 
 def _cached(params, kind, builder):
-    key = params[0]
+    key_t = params[0]
+    kid = id(key_t)
     sig = tuple((p._version, p.data_ptr()) for p in params)
-    slot = _cache.get(key)
-    if slot is None:
-        slot = {}
-        _cache[key] = slot
-    hit = slot.get(kind)
+    ent = _cache.get(kid)
+    if ent is None or ent[0]() is not key_t:
+        ent = (weakref.ref(key_t, lambda _r, kid=kid: _cache.pop(kid, None)), {})
+        _cache[kid] = ent
+    hit = ent[1].get(kind)
     if hit is not None and hit[0] == sig:
         return hit[1]
     val = builder()
-    slot[kind] = (sig, val)
+    ent[1][kind] = (sig, val)
     return val
 
 
