@@ -174,13 +174,60 @@ def f32(t, name='tensor'):
     return t.data_ptr()
 
 
+PROFILER = None   # set to a Profiler() to time every entry point with CUDA events (bench.py)
+
+
+class Profiler:
+    """CUDA-event timing of every C-ABI call on the launching stream (used by bench.py only)."""
+
+    def __init__(self):
+        self.recs = []
+
+    def add(self, name, tag, e0, e1):
+        self.recs.append((name, tag, e0, e1))
+
+    def _ms(self):
+        return [(n, t, e0.elapsed_time(e1)) for (n, t, e0, e1) in self.recs]
+
+    def table(self):
+        out = {}
+        for n, t, ms in self._ms():
+            key = n.replace('effdet_', '')
+            if t is not None:
+                key += ' k%d %d->%d' % (t[5], t[3], t[4])
+            v = out.setdefault(key, [0.0, 0])
+            v[0] += ms
+            v[1] += 1
+        return out
+
+    def conv_flops(self, pred):
+        fl, ms_tot, n = 0.0, 0.0, 0
+        for name, t, ms in self._ms():
+            if name == 'effdet_conv2d' and t is not None and pred(t):
+                fl += 2.0 * t[0] * t[1] * t[2] * t[5] * t[5] * t[3] * t[4]
+                ms_tot += ms
+                n += 1
+        return fl, ms_tot, n
+
+
 def call(name, dev_tensor, *args):
     """Invoke an entry point on dev_tensor's device and the current stream of that device."""
     lib = load()
     dev = dev_tensor.device.index
     if dev is None:
         dev = torch.cuda.current_device()
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    rc = getattr(lib, name)(*args, dev, stream)
+    stream = torch.cuda.current_stream(dev)
+    prof = PROFILER
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+    rc = getattr(lib, name)(*args, dev, stream.cuda_stream)
+    if prof is not None:
+        e1.record(stream)
+        tag = None
+        if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
+            a = args[0]
+            tag = (a.B, a.H, a.W, a.Cin, a.Cout, a.ksize)
+        prof.add(name, tag, e0, e1)
     if rc != 0:
         raise EffdetNativeError('%s failed (%d): %s' % (name, rc, last_error()))
