@@ -10,6 +10,12 @@
 
 namespace effdet {
 
+// tensor-core path (conv_tc.cu)
+bool conv_tc_eligible(const effdet_conv_args* a);
+int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st);
+bool wgrad_tc_eligible(const effdet_wgrad_args* a);
+int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st);
+
 constexpr int kBM = 128;   // output pixels per CTA
 constexpr int kBK = 16;    // reduction slice (channels of one tap)
 constexpr int kNT = 256;   // threads per CTA
@@ -364,6 +370,7 @@ extern "C" int effdet_conv2d(const effdet_conv_args* a, int device, effdet_strea
     const long long Mll = (long long)a->B * a->H * a->W;
     EFFDET_REQUIRE(Mll < (1ll << 31), "conv2d: B*H*W too large");
     const int M = (int)Mll, HW = a->H * a->W;
+    if (conv_tc_eligible(a)) return conv_tc_launch(a, (cudaStream_t)stream);
     // pick the N tile that wastes the fewest padded columns (ties -> wider tile)
     int best = 128;
     long long best_pad = (long long)cdiv(a->Cout, 128) * 128;
@@ -404,6 +411,11 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     EFFDET_REQUIRE(Mll < (1ll << 31), "wgrad: B*H*W too large");
     const int M = (int)Mll, HW = a->H * a->W;
     const int taps = a->ksize * a->ksize;
+    cudaStream_t st = (cudaStream_t)stream;
+    int s = EFFDET_OK;
+    if (wgrad_tc_eligible(a)) {
+        s = wgrad_tc_launch(a, st);
+    } else {
     int BC, BN;
     if (a->Cin <= 32) { BC = 32; BN = 128; }
     else if (a->Cout <= 48) { BC = 128; BN = 32; }
@@ -418,12 +430,12 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     int cps = cdiv(nchunks, splits);
     splits = cdiv(nchunks, cps);
     dim3 grid(ctiles * ntiles, taps, splits);
-    cudaStream_t st = (cudaStream_t)stream;
     if (BC == 32) conv_wgrad_kernel<32, 128, 4, 4><<<grid, kNT, 0, st>>>(*a, M, HW, cps, ctiles);
     else if (BN == 32) conv_wgrad_kernel<128, 32, 4, 4><<<grid, kNT, 0, st>>>(*a, M, HW, cps, ctiles);
     else if (BC == 128) conv_wgrad_kernel<128, 128, 8, 8><<<grid, kNT, 0, st>>>(*a, M, HW, cps, ctiles);
     else conv_wgrad_kernel<64, 64, 4, 4><<<grid, kNT, 0, st>>>(*a, M, HW, cps, ctiles);
-    int s = launch_status("conv_wgrad_kernel");
+    s = launch_status("conv_wgrad_kernel");
+    }
     if (s) return s;
     if (a->dbias) {
         // bias gradient needs dense rows: only valid when dy is contiguous over the batch

@@ -1,0 +1,621 @@
+// tcgen05 tensor-core implicit-GEMM convolution for the dense 3x3 (and 1x1) layers of head and
+// neck: forward, data gradient (same kernel on the rotated/transposed weight pack) and weight
+// gradient.  95 % of the model's FLOPs live here.
+//
+// Precision: operands stay fp32 in HBM (module API parity) and are split on the fly into
+// bf16 hi + bf16 lo (x = hi + lo to 16 mantissa bits); every product is evaluated as
+//   hi*hi + lo*hi + hi*lo      (three kind::f16 MMAs, fp32 accumulation in TMEM)
+// which is ~2^-16 per product -- far inside north_star's 1e-3 where single-pass TF32 is not
+//  -- at 2/3 the cost of 3xTF32.
+//
+// Structure per CTA (192 threads, one 128 x BN output tile, accumulator in TMEM):
+//   warps 0-3  producers: gather the im2col A tile (128 pixels x 64 channels of one tap) with
+//              128-bit loads, split to bf16 hi/lo, store into the canonical K-major SWIZZLE_128B
+//              layout; afterwards the same warps run the epilogue (tcgen05.ld, bias / ReLU /
+//              sigmoid / ReLU-mask / residual, 128-bit stores straight into the caller's layout)
+//   warp 4     TMA: weight tiles (pre-split bf16 planes) -> smem, mbarrier complete_tx
+//   warp 5     one elected thread issues tcgen05.mma; tcgen05.commit frees the smem stage
+// Weight gradient: both operands are produced by the gather warps (pixels are the GEMM-K
+// dimension, so the natural NHWC rows are MN-major operands), split-K over pixel ranges with
+// fp32 atomics into the OIHW gradient.
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace effdet {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 "version 1" (cute::UMMA::SmemDescriptor):
+//   bits [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, majors, N>>3, M>>4
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// split 8 consecutive fp32 values into 8 bf16 "hi" and 8 bf16 "lo" (x ~= hi + lo), 16 bytes each
+__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        const float r0 = f[2 * i] - __low2float(hh), r1 = f[2 * i + 1] - __high2float(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+constexpr int kTcThreads = 192;
+constexpr int kTcProducers = 128;
+constexpr int kTileM = 128;     // pixels per CTA (fwd/dgrad) or output channels per CTA (wgrad)
+constexpr int kTileK = 64;      // bf16 elements per 128-byte swizzled row
+
+// ---------------------------------------------------------------------------------------------
+// forward / data-gradient kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct FwdSmem {
+    static constexpr int kA = kTileM * 128;   // bytes of one bf16 plane of the A tile
+    static constexpr int kB = BN * 128;       // bytes of one bf16 plane of the B tile
+    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
+    using S = FwdSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BN;
+    const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
+    const int KT = taps * kblocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], kTcProducers + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- producers: im2col gather + bf16 split -----------------------------------
+        const int t = threadIdx.x;
+        const int j = t & 7;                 // 16-byte chunk (8 channels) within the 64-channel row
+        long long base[8];
+        int oyx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 16 + (t >> 3);
+            const int m = m0 + r;
+            if (m < M) {
+                const int b = m / HW;
+                const int pix = m - b * HW;
+                const int oy = pix / p.W;
+                oyx[i] = (oy << 16) | (pix - oy * p.W);
+                base[i] = (long long)b * p.x_bstride;
+            } else {
+                oyx[i] = -1;
+                base[i] = 0;
+            }
+        }
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            const int tap = kt / kblocks;
+            const int c = (kt - tap * kblocks) * kTileK + j * 8;
+            const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[2 * i] = f4zero();
+                v[2 * i + 1] = f4zero();
+                if (oyx[i] >= 0 && c < p.Cin) {
+                    const int iy = (oyx[i] >> 16) + ky, ix = (oyx[i] & 0xffff) + kx;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                        const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
+                        v[2 * i] = ldg4(src);
+                        if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
+                    }
+                }
+            }
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_hi = smem + s * S::kStage;
+            uint8_t* a_lo = a_hi + S::kA;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 16 + (t >> 3);
+                uint4 hi, lo;
+                split8(v[2 * i], v[2 * i + 1], hi, lo);
+                const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(a_lo + off) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+        // ---------------- epilogue ------------------------------------------------------------------
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int m = m0 + warp * 32 + lane;
+        const bool row_ok = m < M;
+        int b = 0;
+        long long pix = 0;
+        if (row_ok) {
+            b = m / HW;
+            pix = m - b * HW;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = n0 + cc * 32 + q * 4;
+                if (n >= p.Cout) break;
+                float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
+                                       __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
+                if (p.bias) v = f4add(v, ldg4(p.bias + n));
+                if (p.act == EFFDET_ACT_RELU) {
+                    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+                } else if (p.act == EFFDET_ACT_SIGMOID) {
+                    v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+                } else if (p.act == EFFDET_ACT_SWISH) {
+                    v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+                }
+                if (p.residual) v = f4add(v, ldg4(p.residual + (long long)b * p.r_bstride + pix * p.Cout + n));
+                if (p.mask_src) {
+                    const float4 g = ldg4(p.mask_src + (long long)b * p.m_bstride + pix * p.Cout + n);
+                    v = make_float4(g.x > 0.f ? v.x : 0.f, g.y > 0.f ? v.y : 0.f, g.z > 0.f ? v.z : 0.f,
+                                    g.w > 0.f ? v.w : 0.f);
+                }
+                st4(p.y + (long long)b * p.y_bstride + pix * p.Cout + n, v);
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ---------------- TMA: weight tiles (hi plane, lo plane) ---------------------------------------
+        if (lane == 0) {
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
+                mbar_arrive_expect_tx(&full_bar[s], 2 * S::kB);
+                tma_load_3d(b_hi, &wmap, &full_bar[s], kt * kTileK, n0, 0);
+                tma_load_3d(b_hi + S::kB, &wmap, &full_bar[s], kt * kTileK, n0, 1);
+            }
+        }
+    } else {
+        // ---------------- MMA issue ----------------------------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTileM, BN, 0, 0);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                    const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
+                    const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024), dbl = umma_desc(b_lo + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight-gradient kernel:  D[n, c | tap] += sum_pixels dy[pixel, n] * x[pixel + tap, c]
+//   GEMM-M = 128 output channels, GEMM-N = BC input channels, GEMM-K = pixels (64 per stage);
+//   both operands are NHWC rows (channels contiguous) = MN-major SWIZZLE_128B operands:
+//   one 64-channel group of a stage = 64 pixel-rows x 128 B, groups LBO = 8192 B apart,
+//   8-pixel groups SBO = 1024 B apart.
+// ---------------------------------------------------------------------------------------------
+template <int BC, int STAGES>
+struct WgSmem {
+    static constexpr int kA = kTileK * 128 * (kTileM / 64);   // one plane of the dy tile: 2 channel groups
+    static constexpr int kB = kTileK * 128 * (BC / 64);       // one plane of the x tile
+    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kBytes = STAGES * kStage + 1024 + 256;
+};
+
+// gather `ngroups` channel groups (64 channels each) of 64 pixel rows into swizzled bf16 planes
+template <int NGROUPS>
+__device__ __forceinline__ void wg_produce(const float* __restrict__ src, const long long bstride, const int C, const int c0,
+                                           const int H, const int W, const int HW, const int M, const int mbase, const int dy,
+                                           const int dx, uint8_t* hi_plane, uint8_t* lo_plane, const int t) {
+    // item = (pixel row r, group g, chunk j): 64 * NGROUPS * 8 items over 128 threads
+    constexpr int ITEMS = 64 * NGROUPS * 8 / kTcProducers;
+    const int j = t & 7;
+#pragma unroll 4
+    for (int it = 0; it < ITEMS; ++it) {
+        const int idx = it * kTcProducers + t;
+        const int rg = idx >> 3;                   // r * NGROUPS + g  (g fastest so a warp reads contiguous channels)
+        const int g = rg % NGROUPS, r = rg / NGROUPS;
+        const int m = mbase + r;
+        const int c = c0 + g * 64 + j * 8;
+        float4 v0 = f4zero(), v1 = f4zero();
+        if (m < M && c < C) {
+            const int b = m / HW;
+            const int pix = m - b * HW;
+            const int oy = pix / W;
+            const int iy = oy + dy, ix = pix - oy * W + dx;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                const float* q = src + (long long)b * bstride + ((long long)iy * W + ix) * C + c;
+                v0 = ldg4(q);
+                if (c + 4 < C) v1 = ldg4(q + 4);
+            }
+        }
+        uint4 hi, lo;
+        split8(v0, v1, hi, lo);
+        const int off = g * (kTileK * 128) + r * 128 + ((j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(hi_plane + off) = hi;
+        *reinterpret_cast<uint4*>(lo_plane + off) = lo;
+    }
+}
+
+template <int BC, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wgrad_tc_kernel(const effdet_wgrad_args p, const int M, const int HW, const int chunks_per_split, const int ctiles) {
+    using S = WgSmem<BC, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ct = blockIdx.x % ctiles, nt = blockIdx.x / ctiles;
+    const int c0 = ct * BC, n0 = nt * kTileM;
+    const int tap = blockIdx.y;
+    const int pad = p.ksize / 2;
+    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+    const int nchunks = (M + kTileK - 1) / kTileK;
+    const int ch_begin = blockIdx.z * chunks_per_split;
+    const int ch_end = min(nchunks, ch_begin + chunks_per_split);
+    const int KT = ch_end - ch_begin;      // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], kTcProducers);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<BC>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        const int t = threadIdx.x;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* a_hi = smem + s * S::kStage;
+            uint8_t* b_hi = a_hi + 2 * S::kA;
+            const int mbase = (ch_begin + kt) * kTileK;
+            wg_produce<kTileM / 64>(p.dy, p.dy_bstride, p.Cout, n0, p.H, p.W, HW, M, mbase, 0, 0, a_hi, a_hi + S::kA, t);
+            wg_produce<BC / 64>(p.x, p.x_bstride, p.Cin, c0, p.H, p.W, HW, M, mbase, dy, dx, b_hi, b_hi + S::kB, t);
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+        // epilogue: row = output channel n, columns = input channels c -> atomics into OIHW
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int n = n0 + warp * 32 + lane;
+        const int kk = p.ksize * p.ksize;
+#pragma unroll 1
+        for (int cc = 0; cc < BC / 32; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+            if (n >= p.Cout) continue;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int c = c0 + cc * 32 + q;
+                if (c < p.Cin) atomicAdd(p.dw + ((long long)n * p.Cin + c) * kk + tap, __uint_as_float(acc[q]));
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTileM, BC, 1, 1);
+            constexpr uint32_t LBO = kTileK * 128, SBO = 1024;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                    const uint32_t ko = k * 2 * SBO;     // 16 pixels = two 8-row groups
+                    const uint64_t dah = umma_desc(a_hi + ko, LBO, SBO), dal = umma_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = umma_desc(b_hi + ko, LBO, SBO), dbl = umma_desc(b_lo + ko, LBO, SBO);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<BC>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pre-split: OIHW fp32 -> bf16 planes [2][rows][taps][Kpad] (K-major, zero padded)
+//   forward pack : rows = Cout, k = Cin,  W[n][c][tap]
+//   dgrad pack   : rows = Cin,  k = Cout, W[n][c][taps-1-tap]   (180-degree rotation, transpose)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps,
+                                      int kpad, int dgrad) {
+    const int rows = dgrad ? Cin : Cout;
+    const int kdim = dgrad ? Cout : Cin;
+    const long long plane = (long long)rows * taps * kpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % kpad);
+        const long long r2 = i / kpad;
+        const int tap = (int)(r2 % taps);
+        const int row = (int)(r2 / taps);
+        float v = 0.f;
+        if (k < kdim) {
+            const int n = dgrad ? k : row, c = dgrad ? row : k;
+            const int st = dgrad ? (taps - 1 - tap) : tap;
+            v = __ldg(w + ((long long)n * Cin + c) * taps + st);
+        }
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        out[i] = h;
+        out[plane + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int conv_tc_kpad(int k) { return (k + kTileK - 1) / kTileK * kTileK; }
+
+bool conv_tc_eligible(const effdet_conv_args* a) {
+    return a->w_tc != nullptr && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->scale && !a->a_scale && !a->row_scale && !a->z &&
+           a->Cout >= 16;
+}
+
+int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(EFFDET_ERR_UNSUPPORTED, "conv2d(tc): cuTensorMapEncodeTiled unavailable");
+    const long long Mll = (long long)a->B * a->H * a->W;
+    const int M = (int)Mll, HW = a->H * a->W;
+    const int taps = a->ksize * a->ksize;
+    const int kpad = conv_tc_kpad(a->Cin);
+    const int kblocks = kpad / kTileK;
+    const int BN = a->Cout > 64 ? 256 : 64;
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)taps * kpad, (cuuint64_t)a->Cout, 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)taps * kpad * 2, (cuuint64_t)a->Cout * taps * kpad * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)BN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_tc), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
+    cudaError_t e;
+    if (BN == 256) {
+        constexpr int ST = 2;
+        e = cudaFuncSetAttribute(conv_tc_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<256, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));
+        conv_tc_kernel<256, ST><<<grid, kTcThreads, FwdSmem<256, ST>::kBytes, st>>>(map, *a, M, HW, kblocks);
+    } else {
+        constexpr int ST = 4;
+        e = cudaFuncSetAttribute(conv_tc_kernel<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<64, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));
+        conv_tc_kernel<64, ST><<<grid, kTcThreads, FwdSmem<64, ST>::kBytes, st>>>(map, *a, M, HW, kblocks);
+    }
+    return launch_status("conv_tc_kernel");
+}
+
+bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
+    return a->precision == 1 && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->a_scale && a->Cin >= 32 && a->Cout >= 16;
+}
+
+int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
+    const long long Mll = (long long)a->B * a->H * a->W;
+    const int M = (int)Mll, HW = a->H * a->W;
+    const int taps = a->ksize * a->ksize;
+    const int BC = a->Cin > 64 ? 256 : 64;
+    const int ctiles = cdiv(a->Cin, BC), ntiles = cdiv(a->Cout, kTileM);
+    const int nchunks = cdiv(M, kTileK);
+    int splits = cdiv(148 * 2, ctiles * ntiles * taps);
+    if (splits < 1) splits = 1;
+    if (splits > cdiv(nchunks, 8)) splits = cdiv(nchunks, 8);
+    int cps = cdiv(nchunks, splits);
+    splits = cdiv(nchunks, cps);
+    dim3 grid(ctiles * ntiles, taps, splits);
+    cudaError_t e;
+    if (BC == 256) {
+        constexpr int ST = 2;
+        e = cudaFuncSetAttribute(wgrad_tc_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<256, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc_kernel<256, ST><<<grid, kTcThreads, WgSmem<256, ST>::kBytes, st>>>(*a, M, HW, cps, ctiles);
+    } else {
+        constexpr int ST = 4;
+        e = cudaFuncSetAttribute(wgrad_tc_kernel<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<64, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc_kernel<64, ST><<<grid, kTcThreads, WgSmem<64, ST>::kBytes, st>>>(*a, M, HW, cps, ctiles);
+    }
+    return launch_status("wgrad_tc_kernel");
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_conv_tc_kpad(int channels) { return conv_tc_kpad(channels); }
+
+extern "C" int effdet_pack_conv_weight_tc(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,
+                                          int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(w_oihw && w_fwd && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3), "pack_conv_weight_tc: bad arguments");
+    EFFDET_DEVICE(device);
+    const int taps = ksize * ksize;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        const int kpad = conv_tc_kpad(Cin);
+        const long long plane = (long long)Cout * taps * kpad;
+        int blocks = cdiv(plane, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        pack_weight_tc_kernel<<<blocks, 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_fwd, Cout, Cin, taps, kpad, 0);
+        int s = launch_status("pack_weight_tc_kernel");
+        if (s) return s;
+    }
+    if (w_dgrad) {
+        const int kpad = conv_tc_kpad(Cout);
+        const long long plane = (long long)Cin * taps * kpad;
+        int blocks = cdiv(plane, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        pack_weight_tc_kernel<<<blocks, 256, 0, st>>>(w_oihw, (__nv_bfloat16*)w_dgrad, Cout, Cin, taps, kpad, 1);
+        return launch_status("pack_weight_tc_kernel");
+    }
+    return EFFDET_OK;
+}

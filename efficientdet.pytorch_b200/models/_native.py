@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'stem.cu', 'depthwise.cu', 'mbconv_ops.cu', 'bifpn.cu', 'loss.cu',
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'stem.cu', 'depthwise.cu', 'mbconv_ops.cu', 'bifpn.cu', 'loss.cu',
            'detect.cu', 'layout.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
@@ -54,12 +54,14 @@ class ConvArgs(ctypes.Structure):
     _fields_ = [('x', _P), ('x_bstride', _I64), ('w', _P), ('y', _P), ('y_bstride', _I64), ('z', _P),
                 ('bias', _P), ('scale', _P), ('shift', _P), ('a_scale', _P), ('row_scale', _P),
                 ('residual', _P), ('r_bstride', _I64), ('mask_src', _P), ('m_bstride', _I64),
-                ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32)]
+                ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32),
+                ('w_tc', _P)]
 
 
 class WgradArgs(ctypes.Structure):
     _fields_ = [('x', _P), ('x_bstride', _I64), ('dy', _P), ('dy_bstride', _I64), ('dw', _P), ('dbias', _P),
-                ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32)]
+                ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32),
+                ('precision', _I32)]
 
 
 class BnActBwdArgs(ctypes.Structure):
@@ -87,6 +89,7 @@ SIGNATURES = {
     'effdet_conv2d': [ctypes.POINTER(ConvArgs)] + _TAIL,
     'effdet_conv2d_wgrad': [ctypes.POINTER(WgradArgs)] + _TAIL,
     'effdet_pack_conv_weight': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
+    'effdet_pack_conv_weight_tc': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_colsum': [_P, _P, _I64, _INT] + _TAIL,
     'effdet_stem_fwd': [_P, _P, _P, _P, _P, _P, _INT, _INT, _INT, _INT] + _TAIL,
     'effdet_stem_wgrad': [_P, _P, _P, _INT, _INT, _INT, _INT] + _TAIL,
@@ -112,7 +115,7 @@ SIGNATURES = {
     'effdet_nchw_to_nhwc': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
     'effdet_nhwc_to_nchw': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
 }
-PLAIN = {'effdet_version': (ctypes.c_int, []), 'effdet_last_error': (ctypes.c_char_p, []),
+PLAIN = {'effdet_version': (ctypes.c_int, []), 'effdet_conv_tc_kpad': (ctypes.c_int, [ctypes.c_int]), 'effdet_last_error': (ctypes.c_char_p, []),
          'effdet_launch_count': (ctypes.c_uint64, []), 'effdet_reset_launch_count': (None, [])}
 
 _lib = None

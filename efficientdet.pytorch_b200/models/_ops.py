@@ -7,6 +7,7 @@ so DDP's reducer hooks and ``clip_grad_norm_`` (reference train.py:114-116) keep
 Internal activation layout is NHWC fp32; module boundaries expose the same memory as a logical
 NCHW tensor with channels_last strides (zero-copy ``permute`` views).
 """
+import os
 import weakref
 
 import torch
@@ -105,6 +106,38 @@ def pack_conv(w):
     return _cached([w], 'pack', build)
 
 
+# Precision of the dense 1x1 / 3x3 convolutions of neck and head (95 % of the FLOPs):
+#   'bf16x3' (default): tcgen05 tensor cores, operands split into bf16 hi+lo, three MMAs per product
+#                       (~2^-16 relative per product, fp32 accumulation)
+#   'fp32'            : exact fp32 FMA on the CUDA cores
+PRECISION = os.environ.get('EFFDET_B200_PRECISION', 'bf16x3')
+
+
+def tc_enabled():
+    return PRECISION == 'bf16x3'
+
+
+def pack_conv_tc(w):
+    """OIHW parameter -> (forward, dgrad) pre-split bf16 hi/lo planes for the tensor-core kernels."""
+    def build():
+        Cout, Cin, k, _ = w.shape
+        lib = N.load()
+        kin, kout = lib.effdet_conv_tc_kpad(Cin), lib.effdet_conv_tc_kpad(Cout)
+        src = w.detach().contiguous()
+        tf = torch.empty((2, Cout, k * k, kin), device=w.device, dtype=torch.bfloat16)
+        td = torch.empty((2, Cin, k * k, kout), device=w.device, dtype=torch.bfloat16)
+        N.call('effdet_pack_conv_weight_tc', w, N.f32(src, 'conv weight'), tf.data_ptr(), td.data_ptr(), Cout, Cin, k)
+        return tf, td
+    return _cached([w], 'packtc', build)
+
+
+def tc_packs(w):
+    """(fwd, dgrad) tensor-core packs, or (None, None) when the fp32 path is selected / unsupported."""
+    if not tc_enabled() or w.shape[0] % 4 or w.shape[1] % 4 or w.shape[0] < 16:
+        return None, None
+    return pack_conv_tc(w)
+
+
 def pack_dw(w):
     """[C,1,k,k] depthwise parameter -> [k][k][C]."""
     def build():
@@ -135,15 +168,16 @@ def bn_fold(gamma, beta, rmean, rvar, eps):
 
 def conv2d_raw(dev_t, x_ptr, x_bs, wf, y_ptr, y_bs, B, H, W, Cin, Cout, k, z_ptr=None, bias=None, scale=None,
                shift=None, a_scale=None, row_scale=None, res_ptr=None, res_bs=0, mask_ptr=None, mask_bs=0,
-               act=ACT_NONE):
+               act=ACT_NONE, w_tc=None):
     a = N.ConvArgs(x_ptr, x_bs, N.f32(wf, 'packed weight'), y_ptr, y_bs, z_ptr, N.f32(bias, 'bias'),
                    N.f32(scale, 'scale'), N.f32(shift, 'shift'), N.f32(a_scale, 'a_scale'),
-                   N.f32(row_scale, 'row_scale'), res_ptr, res_bs, mask_ptr, mask_bs, B, H, W, Cin, Cout, k, act)
+                   N.f32(row_scale, 'row_scale'), res_ptr, res_bs, mask_ptr, mask_bs, B, H, W, Cin, Cout, k, act,
+                   w_tc.data_ptr() if w_tc is not None else None)
     N.call('effdet_conv2d', dev_t, a)
 
 
 def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_scale=None, residual=None,
-           mask_src=None, act=ACT_NONE, save_z=False):
+           mask_src=None, act=ACT_NONE, save_z=False, w_tc=None):
     """x NHWC contiguous -> y NHWC (and the raw pre-affine z when save_z)."""
     B, H, W, Cin = x.shape
     y = _empty((B, H, W, Cout), x)
@@ -151,21 +185,21 @@ def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_
     bs = H * W * Cout
     conv2d_raw(x, N.f32(x, 'x'), H * W * Cin, wf, N.f32(y), bs, B, H, W, Cin, Cout, k, z_ptr=N.f32(z), bias=bias,
                scale=scale, shift=shift, a_scale=a_scale, row_scale=row_scale, res_ptr=N.f32(residual, 'residual'),
-               res_bs=bs, mask_ptr=N.f32(mask_src, 'mask_src'), mask_bs=bs, act=act)
+               res_bs=bs, mask_ptr=N.f32(mask_src, 'mask_src'), mask_bs=bs, act=act, w_tc=w_tc)
     return (y, z) if save_z else y
 
 
-def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None):
+def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False):
     a = N.WgradArgs(x_ptr, x_bs, dy_ptr, dy_bs, N.f32(dw, 'dw'), N.f32(dbias, 'dbias'), N.f32(a_scale, 'a_scale'),
-                    B, H, W, Cin, Cout, k)
+                    B, H, W, Cin, Cout, k, 1 if tc else 0)
     N.call('effdet_conv2d_wgrad', dev_t, a)
 
 
-def conv_wgrad(x, dy, dw, dbias, k, a_scale=None):
+def conv_wgrad(x, dy, dw, dbias, k, a_scale=None, tc=False):
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
     conv_wgrad_raw(x, N.f32(x, 'x'), H * W * Cin, N.f32(dy, 'dy'), H * W * Cout, dw, dbias, B, H, W, Cin, Cout, k,
-                   a_scale=a_scale)
+                   a_scale=a_scale, tc=tc)
 
 
 def bnact_bwd(dy, z, scale, shift, mean, rstd, act, row_scale=None, gate=None, dmean=None):
@@ -351,7 +385,7 @@ class ConvBiasActFn(torch.autograd.Function):
         x = _contig(x)
         k = w.shape[2]
         wf, _ = pack_conv(w)
-        y = conv2d(x, wf, w.shape[0], k, bias=b.detach() if b is not None else None, act=act)
+        y = conv2d(x, wf, w.shape[0], k, bias=b.detach() if b is not None else None, act=act, w_tc=tc_packs(w)[0])
         ctx.save_for_backward(x, y if act == ACT_RELU else None)
         ctx.w, ctx.b, ctx.act = w, b, act
         return y
@@ -369,11 +403,11 @@ class ConvBiasActFn(torch.autograd.Function):
         k = w.shape[2]
         dw = torch.zeros_like(w)
         db = torch.zeros_like(b) if b is not None else None
-        conv_wgrad(x, dz, dw, db, k)
+        conv_wgrad(x, dz, dw, db, k, tc=tc_enabled())
         dx = None
         if ctx.needs_input_grad[0]:
             _, wd = pack_conv(w)
-            dx = conv2d(dz, wd, x.shape[3], k)
+            dx = conv2d(dz, wd, x.shape[3], k, w_tc=tc_packs(w)[1])
         return dx, dw, db, None
 
 
@@ -414,7 +448,7 @@ class BiFPNLayerFn(torch.autograd.Function):
 
         def conv(idx, f):
             wf, _ = pack_conv(convs[2 * idx])
-            return conv2d(f, wf, C, 3, bias=convs[2 * idx + 1].detach())
+            return conv2d(f, wf, C, 3, bias=convs[2 * idx + 1].detach(), w_tc=tc_packs(convs[2 * idx])[0])
 
         fused = [None] * (2 * (L - 1))
         td = [None] * L
@@ -451,10 +485,10 @@ class BiFPNLayerFn(torch.autograd.Function):
         def conv_bwd(idx, dy):
             w, b = convs[2 * idx], convs[2 * idx + 1]
             dw, db = torch.zeros_like(w), torch.zeros_like(b)
-            conv_wgrad(fused[idx], dy, dw, db, 3)
+            conv_wgrad(fused[idx], dy, dw, db, 3, tc=tc_enabled())
             dconv[2 * idx], dconv[2 * idx + 1] = dw, db
             _, wd = pack_conv(w)
-            return conv2d(dy, wd, C, 3)
+            return conv2d(dy, wd, C, 3, w_tc=tc_packs(w)[1])
 
         g_in = [None] * L
         g_td = [None] * L
@@ -528,16 +562,16 @@ class RetinaHeadFn(torch.autograd.Function):
             ca, ra = [f], [f]
             for i in range(stacked):
                 wf, _ = pack_conv(cls_p[2 * i])
-                c = conv2d(c, wf, F, 3, bias=cls_p[2 * i + 1].detach(), act=ACT_RELU)
+                c = conv2d(c, wf, F, 3, bias=cls_p[2 * i + 1].detach(), act=ACT_RELU, w_tc=tc_packs(cls_p[2 * i])[0])
                 ca.append(c)
             for i in range(stacked):
                 wf, _ = pack_conv(reg_p[2 * i])
-                r = conv2d(r, wf, F, 3, bias=reg_p[2 * i + 1].detach(), act=ACT_RELU)
+                r = conv2d(r, wf, F, 3, bias=reg_p[2 * i + 1].detach(), act=ACT_RELU, w_tc=tc_packs(reg_p[2 * i])[0])
                 ra.append(r)
             conv2d_raw(f, N.f32(c), H * W * F, wcf, cls_all.data_ptr() + 4 * offs[lv] * K, tot * K, B, H, W, F,
-                       A * K, 3, bias=bc.detach(), act=ACT_SIGMOID)
+                       A * K, 3, bias=bc.detach(), act=ACT_SIGMOID, w_tc=tc_packs(wc)[0])
             conv2d_raw(f, N.f32(r), H * W * F, wrf, reg_all.data_ptr() + 4 * offs[lv] * 4, tot * 4, B, H, W, F,
-                       A * 4, 3, bias=br.detach())
+                       A * 4, 3, bias=br.detach(), w_tc=tc_packs(wr)[0])
             acts.append((ca, ra))
         ctx.meta = (nl, A, K, stacked, offs, tot)
         ctx.keep = (feats, P, acts, cls_all)
@@ -564,23 +598,26 @@ class RetinaHeadFn(torch.autograd.Function):
             _, H, W, Cin = f.shape
             ca, ra = acts[lv]
             outs = []
+            tc = tc_enabled()
             for (tower, tp, tg, wl, gwl, gbl, wld, dptr, width) in (
                     (ca, cls_p, g_cls, wc, gwc, gbc, wcd, dzc.data_ptr() + 4 * offs[lv] * K, K),
                     (ra, reg_p, g_reg, wr, gwr, gbr, wrd, dreg.data_ptr() + 4 * offs[lv] * 4, 4)):
                 top = tower[stacked]
                 Co = A * width
-                conv_wgrad_raw(f, N.f32(top), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3)
+                conv_wgrad_raw(f, N.f32(top), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3, tc=tc)
                 d = _empty((B, H, W, F), f)
                 bs = H * W * F
-                conv2d_raw(f, dptr, tot * width, wld, N.f32(d), bs, B, H, W, Co, F, 3, mask_ptr=N.f32(top), mask_bs=bs)
+                conv2d_raw(f, dptr, tot * width, wld, N.f32(d), bs, B, H, W, Co, F, 3, mask_ptr=N.f32(top), mask_bs=bs,
+                           w_tc=tc_packs(wl)[1])
                 for i in range(stacked - 1, -1, -1):
                     xin = tower[i]
-                    conv_wgrad(xin, d, tg[2 * i], tg[2 * i + 1], 3)
+                    conv_wgrad(xin, d, tg[2 * i], tg[2 * i + 1], 3, tc=tc)
                     _, wd = pack_conv(tp[2 * i])
+                    wdt = tc_packs(tp[2 * i])[1]
                     if i > 0:
-                        d = conv2d(d, wd, F, 3, mask_src=xin)
+                        d = conv2d(d, wd, F, 3, mask_src=xin, w_tc=wdt)
                     else:
-                        d = conv2d(d, wd, Cin, 3, residual=outs[0] if outs else None)
+                        d = conv2d(d, wd, Cin, 3, residual=outs[0] if outs else None, w_tc=wdt)
                 outs.append(d)
             dfeats.append(outs[-1])
         ctx.keep = None

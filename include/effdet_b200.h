@@ -68,6 +68,9 @@ typedef struct {
     const float* residual; int64_t r_bstride;  /* [B,H,W,Cout] added last, or NULL */
     const float* mask_src; int64_t m_bstride;  /* [B,H,W,Cout]: ReLU-backward mask source, or NULL */
     int32_t B, H, W, Cin, Cout, ksize, act;
+    const void* w_tc;      /* optional bf16 hi/lo planes from effdet_pack_conv_weight_tc: when set (and the
+                              epilogue needs only bias/act/residual/mask) the layer runs on the tcgen05
+                              tensor cores as a bf16x3 split-precision implicit GEMM (~2^-16 per product) */
 } effdet_conv_args;
 int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream);
 
@@ -82,6 +85,7 @@ typedef struct {
     float* dbias;     /* [Cout] += , or NULL */
     const float* a_scale;
     int32_t B, H, W, Cin, Cout, ksize;
+    int32_t precision;     /* 0: exact fp32 on the CUDA cores; 1: bf16x3 on the tcgen05 tensor cores */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
 
@@ -89,6 +93,14 @@ int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t 
  * [k*k][Cout][Cin] that turns the data gradient into the same implicit GEMM. */
 int effdet_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, int Cout, int Cin, int ksize,
                             int device, effdet_stream_t stream);
+
+/* OIHW fp32 -> pre-split bf16 planes for the tensor-core path, K-major and zero padded:
+ *   w_fwd   [2][Cout][k*k][kpad(Cin)]   (plane 0 = hi, plane 1 = lo, w ~= hi + lo)
+ *   w_dgrad [2][Cin][k*k][kpad(Cout)]   (rotated 180 degrees and transposed), may be NULL
+ * kpad(c) = effdet_conv_tc_kpad(c) = c rounded up to a multiple of 64. */
+int effdet_conv_tc_kpad(int channels);
+int effdet_pack_conv_weight_tc(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,
+                               int device, effdet_stream_t stream);
 
 /* out[n] += sum_m x[m,n]   (bias gradients, BN beta gradients) */
 int effdet_colsum(const float* x, float* out, int64_t M, int N, int device, effdet_stream_t stream);

@@ -76,6 +76,47 @@ def test_conv2d_forward_dgrad_wgrad(B, H, W, Cin, Cout, k):
     assert _rel(db.cpu(), br.grad) < TOL_EXACT
 
 
+TOL_TC = 3e-5       # bf16x3 split precision on the tensor cores (~2^-16 per product, fp32 accumulate)
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout,k', [
+    (2, 16, 16, 64, 64, 3), (1, 8, 8, 256, 256, 3), (2, 4, 4, 256, 720, 3), (3, 8, 8, 256, 36, 3),
+    (2, 16, 16, 64, 256, 3), (2, 8, 8, 720, 256, 3), (2, 8, 8, 36, 256, 3), (1, 16, 16, 40, 64, 1),
+    (5, 4, 4, 256, 64, 3), (2, 7, 5, 88, 88, 3), (4, 32, 32, 256, 256, 3),
+])
+def test_conv2d_tensor_core_forward_dgrad_wgrad(B, H, W, Cin, Cout, k):
+    """tcgen05 bf16x3 implicit GEMM (fwd, dgrad through the rotated pack, wgrad) vs torch fp32 conv."""
+    ops = _ops()
+    from models._native import ACT_RELU
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout + 7)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    res = torch.randn(B, Cout, H, W, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, 1, k // 2)
+    yr.backward(dy)
+    wp = torch.nn.Parameter(w.to(_dev()))
+    wf, wd = ops.pack_conv(wp)
+    tf, td = ops.pack_conv_tc(wp)
+    xd, dyd = _nhwc(x), _nhwc(dy)
+    y = ops.conv2d(xd, wf, Cout, k, bias=b.to(_dev()), w_tc=tf)
+    e_f = _rel(_nchw(y), yr)
+    y2 = ops.conv2d(xd, wf, Cout, k, bias=b.to(_dev()), act=ACT_RELU, residual=_nhwc(res), mask_src=_nhwc(dy), w_tc=tf)
+    e_e = _rel(_nchw(y2), (torch.relu(yr.detach()) + res) * (dy > 0))
+    dx = ops.conv2d(dyd, wd, Cin, k, w_tc=td)
+    e_d = _rel(_nchw(dx), xr.grad)
+    dw = torch.zeros(Cout, Cin, k, k, device=_dev())
+    db = torch.zeros(Cout, device=_dev())
+    ops.conv_wgrad(xd, dyd, dw, db, k, tc=True)
+    e_w = _rel(dw.cpu(), wr.grad)
+    print('tc conv %s fwd %.2e epi %.2e dgrad %.2e wgrad %.2e' % ((B, H, W, Cin, Cout, k), e_f, e_e, e_d, e_w))
+    assert e_f < TOL_TC and e_e < TOL_TC and e_d < TOL_TC
+    assert e_w < TOL_TC
+    assert _rel(db.cpu(), br.grad) < TOL_EXACT
+
+
 def test_conv2d_epilogue_options():
     ops = _ops()
     from models._native import ACT_RELU, ACT_SIGMOID, ACT_SWISH
