@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
@@ -468,6 +475,181 @@ wgrad_tc_kernel(const effdet_wgrad_args p, const int M, const int HW, const int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// weight-gradient kernel, TMA-fed: the operands were pre-split into bf16 hi/lo planes
+// [2][B][H][W][Cpad] by split_planes_kernel, so the gather warps disappear: one thread issues
+// 5-D tensor-map loads (channel group, x, y, image, plane) whose out-of-bounds zero fill IS the
+// convolution's zero padding (the tap shift is just a coordinate offset), one thread issues the
+// MMAs, four warps drain TMEM into the OIHW gradient with atomics.  A stage covers a box of
+// kstage = Wb*Hb*Bb pixels (<= 64, multiple of 16).
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int conv_tc_kpad(int k) { return (k + kTileK - 1) / kTileK * kTileK; }
+
+struct WgGeom {
+    int Wb, Hb, Bb;          // pixel box of one K stage
+    int nbx, nby, nbb;       // boxes per image row / column / batch
+    int kstage;              // pixels per stage
+};
+
+template <int BC, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const effdet_wgrad_args p,
+                 const WgGeom g, const int chunks_per_split, const int ctiles) {
+    using S = WgSmem<BC, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ct = blockIdx.x % ctiles, nt = blockIdx.x / ctiles;
+    const int c0 = ct * BC, n0 = nt * kTileM;
+    const int tap = blockIdx.y;
+    const int pad = p.ksize / 2;
+    const int dy = tap / p.ksize - pad, dx = tap % p.ksize - pad;
+    const int nchunks = g.nbx * g.nby * g.nbb;
+    const int ch_begin = blockIdx.z * chunks_per_split;
+    const int ch_end = min(nchunks, ch_begin + chunks_per_split);
+    const int KT = ch_end - ch_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<BC>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr int GROUP = kTileK * 128;            // smem slot of one 64-channel group of one plane
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(2 * (kTileM / 64 + BC / 64) * g.kstage * 128);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                int ch = ch_begin + kt;
+                const int bx = ch % g.nbx;
+                ch /= g.nbx;
+                const int by = ch % g.nby;
+                const int bb = ch / g.nby;
+                const int x0 = bx * g.Wb, y0 = by * g.Hb, b0 = bb * g.Bb;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                uint8_t* a_hi = smem + s * S::kStage;
+                uint8_t* b_hi = a_hi + 2 * S::kA;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                    for (int q = 0; q < kTileM / 64; ++q)
+                        tma_load_5d(a_hi + pl * S::kA + q * GROUP, &map_dy, &full_bar[s], n0 + q * 64, x0, y0, b0, pl);
+#pragma unroll
+                    for (int q = 0; q < BC / 64; ++q)
+                        tma_load_5d(b_hi + pl * S::kB + q * GROUP, &map_x, &full_bar[s], c0 + q * 64, x0 + dx, y0 + dy, b0, pl);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTileM, BC, 1, 1);
+            constexpr uint32_t LBO = GROUP, SBO = 1024;
+            const int ksteps = g.kstage / 16;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t ko = k * 2 * SBO;
+                    const uint64_t dah = umma_desc(a_hi + ko, LBO, SBO), dal = umma_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = umma_desc(b_hi + ko, LBO, SBO), dbl = umma_desc(b_lo + ko, LBO, SBO);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int n = n0 + warp * 32 + lane;
+        const int kk = p.ksize * p.ksize;
+#pragma unroll 1
+        for (int cc = 0; cc < BC / 32; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+            if (n >= p.Cout) continue;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int c = c0 + cc * 32 + q;
+                if (c < p.Cin) atomicAdd(p.dw + ((long long)n * p.Cin + c) * kk + tap, __uint_as_float(acc[q]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<BC>(tmem_base);
+    }
+}
+
+// fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, __nv_bfloat16* __restrict__ out,
+                                                           int B, int HW, int C, int Cpad) {
+    const int cv = Cpad / 8;
+    const long long total = (long long)B * HW * cv;
+    const long long plane = (long long)B * HW * Cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % cv);
+        const long long row = i / cv;
+        const int b = (int)(row / HW);
+        const long long pix = row - (long long)b * HW;
+        const int c = j * 8;
+        float4 v0 = f4zero(), v1 = f4zero();
+        if (c < C) {
+            const float* q = x + (long long)b * bstride + pix * C + c;
+            v0 = ldg4(q);
+            if (c + 4 < C) v1 = ldg4(q + 4);
+        }
+        uint4 hi, lo;
+        split8(v0, v1, hi, lo);
+        *reinterpret_cast<uint4*>(out + row * Cpad + c) = hi;
+        *reinterpret_cast<uint4*>(out + plane + row * Cpad + c) = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight pre-split: OIHW fp32 -> bf16 planes [2][rows][taps][Kpad] (K-major, zero padded)
 //   forward pack : rows = Cout, k = Cin,  W[n][c][tap]
 //   dgrad pack   : rows = Cin,  k = Cout, W[n][c][taps-1-tap]   (180-degree rotation, transpose)
@@ -497,25 +679,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-int conv_tc_kpad(int k) { return (k + kTileK - 1) / kTileK * kTileK; }
 
 bool conv_tc_eligible(const effdet_conv_args* a) {
     return a->w_tc != nullptr && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->scale && !a->a_scale && !a->row_scale && !a->z &&
@@ -560,7 +724,84 @@ bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
     return a->precision == 1 && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->a_scale && a->Cin >= 32 && a->Cout >= 16;
 }
 
+static bool wg_geometry(int B, int H, int W, WgGeom* g) {
+    const int Wb = W <= 64 ? W : 64;
+    if (W % Wb) return false;
+    int Hb = 1;
+    for (int h = 1; h <= H && Wb * h <= 64; ++h)
+        if (H % h == 0) Hb = h;
+    int Bb = 64 / (Wb * Hb);
+    if (Bb < 1) Bb = 1;
+    if (Bb > B) Bb = B;
+    const int ks = Wb * Hb * Bb;
+    if (ks < 16 || ks % 16) return false;
+    g->Wb = Wb; g->Hb = Hb; g->Bb = Bb;
+    g->nbx = W / Wb; g->nby = H / Hb; g->nbb = (B + Bb - 1) / Bb;
+    g->kstage = ks;
+    return true;
+}
+
+static int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, int H, int W, int Cpad, const WgGeom& g) {
+    const cuuint64_t gdim[5] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+    const cuuint64_t gstr[4] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2,
+                                (cuuint64_t)B * H * W * Cpad * 2};
+    const cuuint32_t box[5] = {64, (cuuint32_t)g.Wb, (cuuint32_t)g.Hb, (cuuint32_t)g.Bb, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "wgrad(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EFFDET_OK;
+}
+
+// TMA-fed weight gradient; returns 1 when the geometry has no legal pixel box (caller falls back)
+static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
+    WgGeom g;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || !a->ws_x || !a->ws_dy || !wg_geometry(a->B, a->H, a->W, &g)) return 1;
+    const int HW = a->H * a->W;
+    const int cin_pad = conv_tc_kpad(a->Cin), cout_pad = conv_tc_kpad(a->Cout);
+    int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
+    int s = launch_status("split_planes_kernel");
+    if (s) return s;
+    blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
+    if ((s = launch_status("split_planes_kernel"))) return s;
+    CUtensorMap mdy, mx;
+    if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;
+    if ((s = planes_map(enc, &mx, a->ws_x, a->B, a->H, a->W, cin_pad, g))) return s;
+    const int taps = a->ksize * a->ksize;
+    const int BC = a->Cin > 64 ? 256 : 64;
+    const int ctiles = cdiv(a->Cin, BC), ntiles = cdiv(a->Cout, kTileM);
+    const int nchunks = g.nbx * g.nby * g.nbb;
+    int splits = cdiv(148 * 2, ctiles * ntiles * taps);
+    if (splits < 1) splits = 1;
+    if (splits > cdiv(nchunks, 8)) splits = cdiv(nchunks, 8);
+    int cps = cdiv(nchunks, splits);
+    splits = cdiv(nchunks, cps);
+    dim3 grid(ctiles * ntiles, taps, splits);
+    cudaError_t e;
+    if (BC == 256) {
+        constexpr int ST = 2;
+        e = cudaFuncSetAttribute(wgrad_tc2_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<256, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc2_kernel<256, ST><<<grid, kTcThreads, WgSmem<256, ST>::kBytes, st>>>(mdy, mx, *a, g, cps, ctiles);
+    } else {
+        constexpr int ST = 4;
+        e = cudaFuncSetAttribute(wgrad_tc2_kernel<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<64, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc2_kernel<64, ST><<<grid, kTcThreads, WgSmem<64, ST>::kBytes, st>>>(mdy, mx, *a, g, cps, ctiles);
+    }
+    return launch_status("wgrad_tc2_kernel");
+}
+
 int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
+    {
+        const int r = wgrad_tc2_launch(a, st);
+        if (r <= 0) return r;       // launched (0) or failed (<0); 1 = geometry unsupported -> gather kernel
+    }
     const long long Mll = (long long)a->B * a->H * a->W;
     const int M = (int)Mll, HW = a->H * a->W;
     const int taps = a->ksize * a->ksize;

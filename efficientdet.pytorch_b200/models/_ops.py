@@ -190,8 +190,14 @@ def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_
 
 
 def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False):
+    ws_x = ws_dy = None
+    if tc and a_scale is None:
+        lib = N.load()
+        ws_x = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cin),), device=dev_t.device, dtype=torch.bfloat16)
+        ws_dy = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cout),), device=dev_t.device, dtype=torch.bfloat16)
     a = N.WgradArgs(x_ptr, x_bs, dy_ptr, dy_bs, N.f32(dw, 'dw'), N.f32(dbias, 'dbias'), N.f32(a_scale, 'a_scale'),
-                    B, H, W, Cin, Cout, k, 1 if tc else 0)
+                    B, H, W, Cin, Cout, k, 1 if tc else 0, ws_x.data_ptr() if ws_x is not None else None,
+                    ws_dy.data_ptr() if ws_dy is not None else None)
     N.call('effdet_conv2d_wgrad', dev_t, a)
 
 

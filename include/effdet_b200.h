@@ -86,6 +86,9 @@ typedef struct {
     const float* a_scale;
     int32_t B, H, W, Cin, Cout, ksize;
     int32_t precision;     /* 0: exact fp32 on the CUDA cores; 1: bf16x3 on the tcgen05 tensor cores */
+    void* ws_x;            /* precision 1: bf16 workspaces for the pre-split operands, */
+    void* ws_dy;           /*   2*B*H*W*kpad(Cin) resp. 2*B*H*W*kpad(Cout) elements (TMA-fed kernel);
+                              NULL -> the gather-producer tensor-core kernel is used instead */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
 
