@@ -233,7 +233,7 @@ def run_ours(args):
         table = prof.table()
         tot = sum(v[0] for v in table.values())
         breakdown = {k: dict(ms_per_step=round(v[0] / psteps, 4), launches_per_step=v[1] // psteps,
-                             share=round(v[0] / tot, 4)) for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])[:12]}
+                             share=round(v[0] / tot, 4)) for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])[:(200 if args.full_breakdown else 12)]}
         # dominant kernel: the dense 3x3 implicit-GEMM conv (head towers + their dgrad); algorithmic
         # FLOPs = 2*M*9*Cin*Cout per launch, summed over launches, over their summed device time
         fl, t_ms, n = prof.conv_flops(lambda tag: tag[5] == 3 and tag[3] >= 64 and tag[4] >= 36)
@@ -275,6 +275,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--full-breakdown', action='store_true', help='list every kernel class in kernel_breakdown')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

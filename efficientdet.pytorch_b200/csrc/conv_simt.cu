@@ -313,9 +313,10 @@ __global__ void __launch_bounds__(kNT, 2) conv_wgrad_kernel(const effdet_wgrad_a
     }
 }
 
-// out[n] += sum_m x[m][n]
+// out[n] += sum_m x[m][n]   (rows of image b start at x + b*bstride; HW rows per image)
 __global__ void __launch_bounds__(kNT) colsum_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                     const long long M, const int N, const int rows_per_block) {
+                                                     const long long M, const int N, const int rows_per_block,
+                                                     const long long HW, const long long bstride) {
     __shared__ float4 red[kNT];
     const int cvecs = N / 4;
     const RowPack rp = rowpack(cvecs, blockIdx.y);
@@ -323,7 +324,10 @@ __global__ void __launch_bounds__(kNT) colsum_kernel(const float* __restrict__ x
     if (rp.active) {
         const long long r_begin = (long long)blockIdx.x * rows_per_block;
         const long long r_end = min(M, r_begin + rows_per_block);
-        for (long long r = r_begin + rp.tr; r < r_end; r += rp.rows) s = f4add(s, ldg4(x + r * N + rp.cv * 4));
+        for (long long r = r_begin + rp.tr; r < r_end; r += rp.rows) {
+            const long long b = r / HW;
+            s = f4add(s, ldg4(x + b * bstride + (r - b * HW) * N + rp.cv * 4));
+        }
     }
     red[threadIdx.x] = s;
     __syncthreads();
@@ -386,7 +390,15 @@ extern "C" int effdet_conv2d(const effdet_conv_args* a, int device, effdet_strea
     return launch_status("conv_igemm_kernel");
 }
 
+static int colsum_launch(const float* x, float* out, long long M, int N, long long HW, long long bstride, int device,
+                         effdet_stream_t stream);
+
 extern "C" int effdet_colsum(const float* x, float* out, int64_t M, int N, int device, effdet_stream_t stream) {
+    return colsum_launch(x, out, M, N, M, 0, device, stream);
+}
+
+static int colsum_launch(const float* x, float* out, long long M, int N, long long HW, long long bstride, int device,
+                         effdet_stream_t stream) {
     EFFDET_REQUIRE(x && out && M > 0 && N > 0 && N % 4 == 0, "colsum: bad arguments");
     EFFDET_REQUIRE(aligned16(x), "colsum: x must be 16-byte aligned");
     EFFDET_DEVICE(device);
@@ -396,7 +408,7 @@ extern "C" int effdet_colsum(const float* x, float* out, int64_t M, int N, int d
     long long rpb = (M + 148 * 4 - 1) / (148 * 4);
     if (rpb < (long long)rows * 8) rpb = (long long)rows * 8;
     dim3 grid(cdiv(M, rpb), rowpack_chunks(cvecs));
-    colsum_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(x, out, M, N, (int)rpb);
+    colsum_kernel<<<grid, kNT, 0, (cudaStream_t)stream>>>(x, out, M, N, (int)rpb, HW, bstride);
     return launch_status("colsum_kernel");
 }
 
@@ -437,16 +449,7 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     s = launch_status("conv_wgrad_kernel");
     }
     if (s) return s;
-    if (a->dbias) {
-        // bias gradient needs dense rows: only valid when dy is contiguous over the batch
-        if (a->dy_bstride == (long long)HW * a->Cout) {
-            return effdet_colsum(a->dy, a->dbias, M, a->Cout, device, stream);
-        }
-        for (int b = 0; b < a->B; ++b) {
-            s = effdet_colsum(a->dy + (long long)b * a->dy_bstride, a->dbias, HW, a->Cout, device, stream);
-            if (s) return s;
-        }
-    }
+    if (a->dbias) return colsum_launch(a->dy, a->dbias, M, a->Cout, HW, a->dy_bstride, device, stream);
     return EFFDET_OK;
 }
 

@@ -625,8 +625,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
 }
 
 // fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
-__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, __nv_bfloat16* __restrict__ out,
-                                                           int B, int HW, int C, int Cpad) {
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ a_scale,
+                                                           __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad) {
     const int cv = Cpad / 8;
     const long long total = (long long)B * HW * cv;
     const long long plane = (long long)B * HW * Cpad;
@@ -641,6 +641,10 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             const float* q = x + (long long)b * bstride + pix * C + c;
             v0 = ldg4(q);
             if (c + 4 < C) v1 = ldg4(q + 4);
+            if (a_scale) {
+                v0 = f4mul(v0, ldg4(a_scale + (long long)b * C + c));
+                if (c + 4 < C) v1 = f4mul(v1, ldg4(a_scale + (long long)b * C + c + 4));
+            }
         }
         uint4 hi, lo;
         split8(v0, v1, hi, lo);
@@ -720,8 +724,13 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
     return launch_status("conv_tc_kernel");
 }
 
+static bool wg_geometry(int B, int H, int W, WgGeom* g);
+
 bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
-    return a->precision == 1 && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->a_scale && a->Cin >= 32 && a->Cout >= 16;
+    if (a->precision != 1 || a->Cin % 4 || a->Cout % 4 || a->Cin < 16 || a->Cout < 16) return false;
+    WgGeom g;
+    const bool tma_ok = a->ws_x && a->ws_dy && wg_geometry(a->B, a->H, a->W, &g);
+    return tma_ok || !a->a_scale;     // the gather-producer fallback has no input gate
 }
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g) {
@@ -762,12 +771,12 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     const int cin_pad = conv_tc_kpad(a->Cin), cout_pad = conv_tc_kpad(a->Cout);
     int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
+    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
     int s = launch_status("split_planes_kernel");
     if (s) return s;
     blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
+    split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, nullptr, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
     if ((s = launch_status("split_planes_kernel"))) return s;
     CUtensorMap mdy, mx;
     if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;

@@ -191,7 +191,7 @@ def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_
 
 def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False):
     ws_x = ws_dy = None
-    if tc and a_scale is None:
+    if tc:
         lib = N.load()
         ws_x = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cin),), device=dev_t.device, dtype=torch.bfloat16)
         ws_dy = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cout),), device=dev_t.device, dtype=torch.bfloat16)
@@ -342,7 +342,7 @@ class MBConvFn(torch.autograd.Function):
         dz2, dg2, db2 = bnact_bwd(dy, t['z2'], t['sc2'], t['sh2'], t['rm2'], t['rs2'], ACT_NONE,
                                   row_scale=t['row_scale'])
         dWp = torch.zeros_like(Wp)
-        conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate)
+        conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate, tc=tc_enabled())
         _, wpd = pack_conv(Wp)
         dq = conv2d(dz2, wpd, C, 1)                      # grad w.r.t. (a1 * gate)
         # squeeze-excite backward
@@ -369,7 +369,7 @@ class MBConvFn(torch.autograd.Function):
             We = P[0]
             dz0, dg0, db0 = bnact_bwd(da0, t['z0'], t['sc0'], t['sh0'], t['rm0'], t['rs0'], ACT_SWISH)
             dWe = torch.zeros_like(We)
-            conv_wgrad(x, dz0, dWe, None, 1)
+            conv_wgrad(x, dz0, dWe, None, 1, tc=tc_enabled())
             _, wed = pack_conv(We)
             dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None)
             grads += [dWe, dg0, db0, None, None]
