@@ -234,15 +234,26 @@ def run_ours(args):
         tot = sum(v[0] for v in table.values())
         breakdown = {k: dict(ms_per_step=round(v[0] / psteps, 4), launches_per_step=v[1] // psteps,
                              share=round(v[0] / tot, 4)) for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])[:(200 if args.full_breakdown else 12)]}
-        # dominant kernel: the dense 3x3 implicit-GEMM conv (head towers + their dgrad); algorithmic
-        # FLOPs = 2*M*9*Cin*Cout per launch, summed over launches, over their summed device time
-        fl, t_ms, n = prof.conv_flops(lambda tag: tag[5] == 3 and tag[3] >= 64 and tag[4] >= 36)
+        # dominant kernel class: the dense 3x3 implicit-GEMM conv of head + neck (forward and data-gradient
+        # launches of conv_tc_kernel / conv_igemm_kernel).  Algorithmic FLOPs = 2*M*9*Cin*Cout per launch
+        # (SURVEY.md 8(d)), summed over the launches of the profiled steps, over their summed device time
+        # (CUDA events on the launching stream around every C-ABI call).
+        fl, t_ms, n = prof.conv_flops(lambda tag: tag[5] == 3 and tag[3] >= 36 and tag[4] >= 36)
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms else 0.0
-        roofline = dict(kernel='conv_igemm_kernel (dense 3x3 implicit GEMM, neck+head fwd+dgrad, fp32 CUDA cores)',
-                        bound='tensor', achieved=round(ach, 2), peak=peaks['bf16_tflops_sustained'] or peaks['bf16_tflops'],
-                        unit='TFLOP/s', frac=round(ach / (peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']), 4),
-                        peak_source=peaks['source'] + ' (sustained bf16 cuBLAS; kernel timed inside a long step)',
-                        launches_per_step=n // psteps, ms_per_step=round(t_ms / psteps, 3), traffic=None)
+        tc = _ops.tc_enabled()
+        peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
+        roofline = dict(kernel=('conv_tc_kernel: tcgen05 bf16x3 implicit GEMM (3 kind::f16 MMAs per product, fp32 accum in TMEM), '
+                                'dense 3x3 convs of head+neck, fwd+dgrad' if tc else
+                                'conv_igemm_kernel: exact fp32 on the CUDA cores, dense 3x3 convs of head+neck, fwd+dgrad'),
+                        bound='tensor', achieved=round(ach, 2), peak=peak, unit='TFLOP/s', frac=round(ach / peak, 4),
+                        peak_source=peaks['source'] + ' bf16 cuBLAS, sustained figure (kernel timed inside a long step)',
+                        note=('achieved counts ALGORITHMIC fp32-equivalent FLOPs; the tensor pipe executes 3x that '
+                              '(bf16 hi/lo split for <=1e-3 parity): tensor-pipe work = %.0f TFLOP/s = %.2f of peak'
+                              % (3 * ach, 3 * ach / peak)) if tc else None,
+                        launches_per_step=n // psteps, ms_per_step=round(t_ms / psteps, 3),
+                        traffic=dict(per_launch_bytes=223.0e6, algorithmic_bytes=268.4e6,
+                                     source='ncu --set full, P3 256->256 launch: dram read 136.8 MB + write 86.2 MB '
+                                            '(profiles/r01_ncu_conv_tc_kernel_p3.txt)') if tc else None)
         if not args.no_cpu:
             cores = usable_cores()
             ips, dt = cpu_reference_steps(4, 2, 1, cores)
@@ -253,7 +264,7 @@ def run_ours(args):
         imgs = BS * world * args.steps
         line = dict(metric=METRIC, value=round(imgs / (ms * 1e-3), 2), unit='img/s', n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling='weak',
-                    vs_baseline=None, dtype='f32', data='synthetic',
+                    vs_baseline=None, dtype='f32 (I/O and accumulation; dense convs bf16x3-split on tensor cores)' if _ops.tc_enabled() else 'f32', data='synthetic',
                     config=dict(workload='EfficientDet-D0 512x512 K=80 bs=32/GPU train step fwd+bwd (configs[1]; configs[2] when N=8)',
                                 global_batch=BS * world, parallelism='dp%d' % world,
                                 l2='per-step working set (~20 GB of activations) >> 126 MB L2; no explicit flush',

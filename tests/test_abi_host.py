@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the shared object loads and exports every symbol the header
+declares, the nn.Module mirror has the reference's state-dict schema, and the product refuses to run
+without CUDA tensors (no silent fallback).  No GPU needed, no compute calls."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import effdet_oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def native():
+    from models import _native
+    _native.build()
+    return _native
+
+
+def test_shared_object_exports_every_declared_symbol(native):
+    hdr = open(os.path.join(REPO, 'include', 'effdet_b200.h')).read()
+    declared = set(re.findall(r'\b(effdet_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'effdet_stream_t'}
+    out = subprocess.run(['nm', '-D', '--defined-only', native.SO_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r' T (effdet_[a-z0-9_]+)', out))
+    assert declared, 'header parse failed'
+    assert declared <= exported, 'declared but not exported: %s' % sorted(declared - exported)
+    bound = set(native.SIGNATURES) | set(native.PLAIN)
+    assert declared == bound, 'header vs ctypes binding mismatch: %s' % sorted(declared ^ bound)
+    lib = native.load()
+    assert lib.effdet_version() >= 100
+    assert lib.effdet_conv_tc_kpad(36) == 64 and lib.effdet_conv_tc_kpad(720) == 768
+
+
+def test_ctypes_struct_layout_matches_header(native):
+    import ctypes
+    # pointer/int64 fields first, int32 tail: sizes as the C compiler lays them out on LP64
+    assert ctypes.sizeof(native.ConvArgs) == 15 * 8 + 7 * 4 + 4 + 8
+    assert ctypes.sizeof(native.WgradArgs) == 7 * 8 + 7 * 4 + 4 + 2 * 8
+    assert ctypes.sizeof(native.BnActBwdArgs) == 12 * 8 + 4 + 4 * 4 + 4
+    assert ctypes.sizeof(native.FuseArgs) == 4 * 8 + 4 + 4 + 8 + 5 * 4 + 4
+    assert ctypes.sizeof(native.FuseBwdArgs) == 5 * 8 + 4 + 4 + 3 * 8 + 3 * 4 + 4 + 2 * 8 + 5 * 4 + 4
+
+
+@pytest.mark.parametrize('net,W,D', [('efficientdet-d0', 64, 2), ('efficientdet-d3', 160, 5)])
+def test_state_dict_schema_matches_reference(net, W, D):
+    from models import EfficientDet
+    m = EfficientDet(num_classes=20, network=net, D_bifpn=D, W_bifpn=W)
+    cfg = O.make_config(net, 20, W, D)
+    spec = O.state_dict_spec(cfg)          # pinned to the reference by tests/golden/make_golden.py
+    sd = m.state_dict()
+    assert list(sd.keys()) == [s[0] for s in spec]
+    for name, shape, _ in spec:
+        assert tuple(sd[name].shape) == tuple(shape), name
+    # constructor side effects of the reference (models/efficientdet.py:47-55)
+    assert all(not mod.training for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d))
+    assert m.is_training is True and m.threshold == 0.01 and m.iou_threshold == 0.5
+    assert m.backbone.get_list_features()[-5:] == cfg['stage_out'][-5:]
+
+
+def test_no_cpu_fallback():
+    from models import EfficientDet
+    from models._native import EffdetNativeError
+    m = EfficientDet(num_classes=20, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=False)
+    with pytest.raises(EffdetNativeError):
+        m(torch.zeros(1, 3, 128, 128))
+    from models.losses import FocalLoss
+    with pytest.raises(EffdetNativeError):
+        FocalLoss()(torch.zeros(1, 9, 4), torch.zeros(1, 9, 4), torch.zeros(1, 9, 4), torch.zeros(1, 1, 5))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(REPO, 'efficientdet.pytorch_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(root, f)).read()
+                assert 'effdet_oracle' not in src and 'oracle' not in src.replace('oracle/', ''), os.path.join(root, f)
+
+
+def test_anchor_table_is_bit_exact_on_host():
+    from models.module import _anchor_table, Anchors
+    a = Anchors()
+    for (h, w) in [(512, 512), (384, 640), (1536, 1536)]:
+        tab = _anchor_table(h, w, a.pyramid_levels, a.strides, a.sizes, a.ratios, a.scales)
+        assert (tab == O.anchors_for(h, w)).all()
