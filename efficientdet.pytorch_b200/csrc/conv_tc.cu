@@ -152,7 +152,7 @@ struct FwdSmem {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, (STAGES == 1 ? 2 : 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -219,6 +219,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                         const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
                         v[2 * i] = ldg4(src);
                         if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
+                        if (p.a_scale) {                       // squeeze-excite gate on the input (per image, channel)
+                            const float* gp = p.a_scale + (base[i] / p.x_bstride) * p.Cin + c;
+                            v[2 * i] = f4mul(v[2 * i], ldg4(gp));
+                            if (c + 4 < p.Cin) v[2 * i + 1] = f4mul(v[2 * i + 1], ldg4(gp + 4));
+                        }
                     }
                 }
             }
@@ -248,8 +253,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             b = m / HW;
             pix = m - b * HW;
         }
+        const float rs = (row_ok && p.row_scale) ? __ldg(p.row_scale + b) : 1.f;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
+            if (n0 + cc * 32 >= p.Cout) break;           // warp-uniform: nothing left in this tile
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
             if (!row_ok) continue;
@@ -260,6 +267,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
                                        __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
                 if (p.bias) v = f4add(v, ldg4(p.bias + n));
+                if (p.z) st4(p.z + (long long)b * p.y_bstride + pix * p.Cout + n, v);
+                if (p.scale) v = f4fma(v, ldg4(p.scale + n), ldg4(p.shift + n));
                 if (p.act == EFFDET_ACT_RELU) {
                     v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
                 } else if (p.act == EFFDET_ACT_SIGMOID) {
@@ -267,6 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 } else if (p.act == EFFDET_ACT_SWISH) {
                     v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
                 }
+                if (p.row_scale) v = f4scale(v, rs);
                 if (p.residual) v = f4add(v, ldg4(p.residual + (long long)b * p.r_bstride + pix * p.Cout + n));
                 if (p.mask_src) {
                     const float4 g = ldg4(p.mask_src + (long long)b * p.m_bstride + pix * p.Cout + n);
@@ -686,8 +696,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 
 
 bool conv_tc_eligible(const effdet_conv_args* a) {
-    return a->w_tc != nullptr && a->Cin % 4 == 0 && a->Cout % 4 == 0 && !a->scale && !a->a_scale && !a->row_scale && !a->z &&
-           a->Cout >= 16;
+    return a->w_tc != nullptr && a->Cin % 4 == 0 && a->Cout % 4 == 0 && a->Cout >= 16;
 }
 
 int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
@@ -698,7 +707,8 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
     const int taps = a->ksize * a->ksize;
     const int kpad = conv_tc_kpad(a->Cin);
     const int kblocks = kpad / kTileK;
-    const int BN = a->Cout > 64 ? 256 : 64;
+    const int KT = taps * kblocks;
+    const int BN = a->Cout <= 64 ? 64 : (a->Cout <= 128 ? 128 : 256);
     CUtensorMap map;
     const cuuint64_t gdim[3] = {(cuuint64_t)taps * kpad, (cuuint64_t)a->Cout, 2};
     const cuuint64_t gstr[2] = {(cuuint64_t)taps * kpad * 2, (cuuint64_t)a->Cout * taps * kpad * 2};
@@ -709,18 +719,25 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
     dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
-    cudaError_t e;
-    if (BN == 256) {
-        constexpr int ST = 2;
-        e = cudaFuncSetAttribute(conv_tc_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<256, ST>::kBytes);
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));
-        conv_tc_kernel<256, ST><<<grid, kTcThreads, FwdSmem<256, ST>::kBytes, st>>>(map, *a, M, HW, kblocks);
+#define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
+    do {                                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                             FwdSmem<BN_, ST_>::kBytes);                                                  \
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
+        conv_tc_kernel<BN_, ST_><<<grid, kTcThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);           \
+    } while (0)
+    // short reductions (1x1 convs of the backbone): single-stage instances so 2-3 CTAs share an SM and hide each
+    // other's prologue / epilogue; long reductions: deep pipelines, one CTA per SM
+    if (KT <= 2) {
+        if (BN == 64) EFFDET_TC_LAUNCH(64, 1);
+        else if (BN == 128) EFFDET_TC_LAUNCH(128, 1);
+        else EFFDET_TC_LAUNCH(256, 1);
     } else {
-        constexpr int ST = 4;
-        e = cudaFuncSetAttribute(conv_tc_kernel<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem<64, ST>::kBytes);
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));
-        conv_tc_kernel<64, ST><<<grid, kTcThreads, FwdSmem<64, ST>::kBytes, st>>>(map, *a, M, HW, kblocks);
+        if (BN == 64) EFFDET_TC_LAUNCH(64, 4);
+        else if (BN == 128) EFFDET_TC_LAUNCH(128, 3);
+        else EFFDET_TC_LAUNCH(256, 2);
     }
+#undef EFFDET_TC_LAUNCH
     return launch_status("conv_tc_kernel");
 }
 

@@ -289,7 +289,8 @@ class MBConvFn(torch.autograd.Function):
             i = 5
             sc0, sh0, rs0 = bn_fold(g0, b0, rm0, rv0, eps)
             wf, _ = pack_conv(We)
-            a0, z0 = conv2d(x, wf, We.shape[0], 1, scale=sc0, shift=sh0, act=ACT_SWISH, save_z=True)
+            a0, z0 = conv2d(x, wf, We.shape[0], 1, scale=sc0, shift=sh0, act=ACT_SWISH, save_z=True,
+                            w_tc=tc_packs(We)[0])
             saved.update(z0=z0, sc0=sc0, sh0=sh0, rs0=rs0, rm0=rm0)
         else:
             a0 = x
@@ -319,7 +320,8 @@ class MBConvFn(torch.autograd.Function):
         Cout = Wp.shape[0]
         skip = cfg['skip']
         y, z2 = conv2d(a1, wpf, Cout, 1, scale=sc2, shift=sh2, a_scale=gate,
-                       row_scale=row_scale if skip else None, residual=x if skip else None, save_z=True)
+                       row_scale=row_scale if skip else None, residual=x if skip else None, save_z=True,
+                       w_tc=tc_packs(Wp)[0])
         ctx.cfg = cfg
         ctx.P = P
         ctx.t = dict(saved, x=x, a0=a0, z1=z1, a1=a1, mean=mean, s_pre=s_pre, gate=gate, z2=z2, sc1=sc1, sh1=sh1,
@@ -344,7 +346,7 @@ class MBConvFn(torch.autograd.Function):
         dWp = torch.zeros_like(Wp)
         conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate, tc=tc_enabled())
         _, wpd = pack_conv(Wp)
-        dq = conv2d(dz2, wpd, C, 1)                      # grad w.r.t. (a1 * gate)
+        dq = conv2d(dz2, wpd, C, 1, w_tc=tc_packs(Wp)[1])     # grad w.r.t. (a1 * gate)
         # squeeze-excite backward
         dgate = _zeros((B, C), x)
         N.call('effdet_spatial_reduce', x, N.f32(dq), N.f32(a1), N.f32(dgate), 1.0, B, Ho * Wo, C)
@@ -371,7 +373,7 @@ class MBConvFn(torch.autograd.Function):
             dWe = torch.zeros_like(We)
             conv_wgrad(x, dz0, dWe, None, 1, tc=tc_enabled())
             _, wed = pack_conv(We)
-            dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None)
+            dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
             grads += [dWe, dg0, db0, None, None]
         else:
             dx = add(da0, dy) if cfg['skip'] else da0
