@@ -101,36 +101,51 @@ __global__ void __launch_bounds__(256) dw_bwd_data_kernel(const float* __restric
 }
 
 // dw[c][ky][kx] += sum_{b,oy,ox} x[b,oy*S+ky-pt,ox*S+kx-pl,c] * dz[b,oy,ox,c]
+// Each thread owns 4 channels and walks strips of kTW consecutive outputs: per kernel row it fetches the
+// (kTW-1)*S+K input columns once and reuses them for all K taps of all kTW outputs (2.4x fewer loads than one
+// fetch per tap for k5).  Per-thread partial sums live in registers, one shared-memory reduction + atomics at the end.
 template <int K, int S>
 __global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                             float* __restrict__ dw, int B, int H, int W, int C, int pad_t,
                                                             int pad_l, int Ho, int Wo, int rows_per_block) {
     __shared__ float4 red[256];
+    constexpr int NCOL = (kTW - 1) * S + K;
     const int cvecs = C / 4;
     const RowPack rp = rowpack(cvecs, blockIdx.y);
     float4 acc[K * K];
 #pragma unroll
     for (int i = 0; i < K * K; ++i) acc[i] = f4zero();
-    const long long npix = (long long)B * Ho * Wo;
+    const int wgroups = (Wo + kTW - 1) / kTW;
+    const long long ngroups = (long long)B * Ho * wgroups;
     if (rp.active) {
         const long long r_begin = (long long)blockIdx.x * rows_per_block;
-        const long long r_end = min(npix, r_begin + rows_per_block);
-        for (long long pr = r_begin + rp.tr; pr < r_end; pr += rp.rows) {
-            const int ox = (int)(pr % Wo);
-            const long long q = pr / Wo;
+        const long long r_end = min(ngroups, r_begin + rows_per_block);
+        for (long long gi = r_begin + rp.tr; gi < r_end; gi += rp.rows) {
+            const int og = (int)(gi % wgroups);
+            const long long q = gi / wgroups;
             const int oy = (int)(q % Ho);
             const int b = (int)(q / Ho);
-            const float4 g = ldg4(dz + pr * C + rp.cv * 4);
+            const int ox0 = og * kTW;
+            float4 g[kTW];
+            const float* gp = dz + (((long long)b * Ho + oy) * Wo + ox0) * C + rp.cv * 4;
+#pragma unroll
+            for (int t = 0; t < kTW; ++t) g[t] = (ox0 + t < Wo) ? ldg4(gp + (long long)t * C) : f4zero();
             const float* xb = x + (long long)b * H * W * C + rp.cv * 4;
 #pragma unroll
             for (int ky = 0; ky < K; ++ky) {
                 const int iy = oy * S + ky - pad_t;
                 if (iy < 0 || iy >= H) continue;
+                const float* xr = xb + (long long)iy * W * C;
 #pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    const int ix = ox * S + kx - pad_l;
-                    if (ix < 0 || ix >= W) continue;
-                    acc[ky * K + kx] = f4fma(ldg4(xb + ((long long)iy * W + ix) * C), g, acc[ky * K + kx]);
+                for (int j = 0; j < NCOL; ++j) {
+                    const int ix = ox0 * S + j - pad_l;
+                    float4 v = f4zero();
+                    if (ix >= 0 && ix < W) v = ldg4(xr + (long long)ix * C);
+#pragma unroll
+                    for (int t = 0; t < kTW; ++t) {
+                        const int kx = j - t * S;
+                        if (kx >= 0 && kx < K) acc[ky * K + kx] = f4fma(v, g[t], acc[ky * K + kx]);
+                    }
                 }
             }
         }
@@ -212,10 +227,10 @@ extern "C" int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* 
     if (s) return s;
     EFFDET_DEVICE(device);
     const int cvecs = C / 4;
-    const long long npix = (long long)B * Ho * Wo;
+    const long long npix = (long long)B * Ho * cdiv(Wo, kTW);   // strips of kTW outputs
     const int rows = rowpack_rows(cvecs);
-    long long rpb = (npix + 148 * 4 - 1) / (148 * 4);
-    if (rpb < (long long)rows * 4) rpb = (long long)rows * 4;
+    long long rpb = (npix + 148 * 2 - 1) / (148 * 2);
+    if (rpb < (long long)rows * 2) rpb = (long long)rows * 2;
     dim3 grid(cdiv(npix, rpb), rowpack_chunks(cvecs));
     cudaStream_t st = (cudaStream_t)stream;
     DW_DISPATCH(dw_bwd_weight_kernel, <<<grid, 256, 0, st>>>(x, dz, dw_c1kk, B, H, W, C, pad_t, pad_l, Ho, Wo, (int)rpb))
