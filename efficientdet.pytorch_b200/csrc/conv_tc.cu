@@ -151,7 +151,8 @@ struct FwdSmem {
     static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES>
+// MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
+template <int BN, int STAGES, bool MB>
 __global__ void __launch_bounds__(kTcThreads, (STAGES == 1 ? 2 : 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
     using S = FwdSmem<BN, STAGES>;
@@ -202,13 +203,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 base[i] = 0;
             }
         }
-        for (int kt = 0; kt < KT; ++kt) {
-            const int s = kt % STAGES;
-            const uint32_t ph = (kt / STAGES) & 1;
+        // gather one stage worth of fp32 operands into registers (8 rows x 32 bytes per thread)
+        auto load_stage = [&](int kt, float4 (&v)[16]) {
             const int tap = kt / kblocks;
             const int c = (kt - tap * kblocks) * kTileK + j * 8;
             const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
-            float4 v[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 v[2 * i] = f4zero();
@@ -219,7 +218,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                         const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
                         v[2 * i] = ldg4(src);
                         if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
-                        if (p.a_scale) {                       // squeeze-excite gate on the input (per image, channel)
+                        if (MB && p.a_scale) {                 // squeeze-excite gate on the input (per image, channel)
                             const float* gp = p.a_scale + (base[i] / p.x_bstride) * p.Cin + c;
                             v[2 * i] = f4mul(v[2 * i], ldg4(gp));
                             if (c + 4 < p.Cin) v[2 * i + 1] = f4mul(v[2 * i + 1], ldg4(gp + 4));
@@ -227,6 +226,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                     }
                 }
             }
+        };
+        // split to bf16 hi/lo and publish the stage to the MMA warp
+        auto store_stage = [&](int kt, const float4 (&v)[16]) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* a_hi = smem + s * S::kStage;
             uint8_t* a_lo = a_hi + S::kA;
@@ -241,6 +245,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             }
             fence_proxy_async();
             mbar_arrive(&full_bar[s]);
+        };
+        // software pipeline: the loads of stage kt+1 are in flight while stage kt is converted and stored
+        float4 va[16], vb[16];
+        load_stage(0, va);
+        for (int kt = 0; kt < KT; kt += 2) {
+            if (kt + 1 < KT) load_stage(kt + 1, vb);
+            store_stage(kt, va);
+            if (kt + 1 < KT) {
+                if (kt + 2 < KT) load_stage(kt + 2, va);
+                store_stage(kt + 1, vb);
+            }
         }
         // ---------------- epilogue ------------------------------------------------------------------
         mbar_wait(accum_bar, 0);
@@ -253,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             b = m / HW;
             pix = m - b * HW;
         }
-        const float rs = (row_ok && p.row_scale) ? __ldg(p.row_scale + b) : 1.f;
+        const float rs = (MB && row_ok && p.row_scale) ? __ldg(p.row_scale + b) : 1.f;
 #pragma unroll 1
         for (int cc = 0; cc < BN / 32; ++cc) {
             if (n0 + cc * 32 >= p.Cout) break;           // warp-uniform: nothing left in this tile
@@ -267,8 +282,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
                                        __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
                 if (p.bias) v = f4add(v, ldg4(p.bias + n));
-                if (p.z) st4(p.z + (long long)b * p.y_bstride + pix * p.Cout + n, v);
-                if (p.scale) v = f4fma(v, ldg4(p.scale + n), ldg4(p.shift + n));
+                if (MB && p.z) st4(p.z + (long long)b * p.y_bstride + pix * p.Cout + n, v);
+                if (MB && p.scale) v = f4fma(v, ldg4(p.scale + n), ldg4(p.shift + n));
                 if (p.act == EFFDET_ACT_RELU) {
                     v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
                 } else if (p.act == EFFDET_ACT_SIGMOID) {
@@ -276,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 } else if (p.act == EFFDET_ACT_SWISH) {
                     v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
                 }
-                if (p.row_scale) v = f4scale(v, rs);
+                if (MB && p.row_scale) v = f4scale(v, rs);
                 if (p.residual) v = f4add(v, ldg4(p.residual + (long long)b * p.r_bstride + pix * p.Cout + n));
                 if (p.mask_src) {
                     const float4 g = ldg4(p.mask_src + (long long)b * p.m_bstride + pix * p.Cout + n);
@@ -696,7 +711,10 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 
 
 bool conv_tc_eligible(const effdet_conv_args* a) {
-    return a->w_tc != nullptr && a->Cin % 4 == 0 && a->Cout % 4 == 0 && a->Cout >= 16;
+    if (a->w_tc == nullptr || a->Cin % 4 || a->Cout % 4 || a->Cout < 16) return false;
+    // measured (profiles/r01_bench_full_breakdown.json): the narrowest 1x1 layers are faster on the CUDA cores
+    if (a->ksize == 1 && (a->Cin < 24 || (a->Cin <= 32 && a->Cout <= 16))) return false;
+    return true;
 }
 
 int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
@@ -719,12 +737,18 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
     dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
-#define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
+    const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
+#define EFFDET_TC_LAUNCH1(BN_, ST_, MB_)                                                                                   \
     do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
-        conv_tc_kernel<BN_, ST_><<<grid, kTcThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);           \
+        conv_tc_kernel<BN_, ST_, MB_><<<grid, kTcThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
+    } while (0)
+#define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
+    do {                                                                                                                  \
+        if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true);                                                                        \
+        else EFFDET_TC_LAUNCH1(BN_, ST_, false);                                                                          \
     } while (0)
     // short reductions (1x1 convs of the backbone): single-stage instances so 2-3 CTAs share an SM and hide each
     // other's prologue / epilogue; long reductions: deep pipelines, one CTA per SM
@@ -738,6 +762,7 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
         else EFFDET_TC_LAUNCH(256, 2);
     }
 #undef EFFDET_TC_LAUNCH
+#undef EFFDET_TC_LAUNCH1
     return launch_status("conv_tc_kernel");
 }
 
