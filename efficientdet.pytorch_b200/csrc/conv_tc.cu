@@ -135,8 +135,10 @@ __device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 192;        // weight-gradient kernels: 4 gather/epilogue warps + TMA + MMA
 constexpr int kTcProducers = 128;
+constexpr int kFwdThreads = 320;       // forward/dgrad kernel: 8 gather/epilogue warps + TMA + MMA
+constexpr int kFwdProducers = 256;
 constexpr int kTileM = 128;     // pixels per CTA (fwd/dgrad) or output channels per CTA (wgrad)
 constexpr int kTileK = 64;      // bf16 elements per 128-byte swizzled row
 
@@ -153,7 +155,7 @@ struct FwdSmem {
 
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
 template <int BN, int STAGES, bool MB>
-__global__ void __launch_bounds__(kTcThreads, (STAGES == 1 ? 2 : 1))
+__global__ void __launch_bounds__(kFwdThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
@@ -170,27 +172,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], kTcProducers + 1);
+            mbar_init(&full_bar[s], kFwdProducers + 1);
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<BN>(tmem_slot);
+    if (warp == 8) tmem_alloc<BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ---------------- producers: im2col gather + bf16 split -----------------------------------
         const int t = threadIdx.x;
         const int j = t & 7;                 // 16-byte chunk (8 channels) within the 64-channel row
-        long long base[8];
-        int oyx[8];
+        long long base[4];
+        int oyx[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = i * 16 + (t >> 3);
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 32 + (t >> 3);
             const int m = m0 + r;
             if (m < M) {
                 const int b = m / HW;
@@ -203,13 +205,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 base[i] = 0;
             }
         }
-        // gather one stage worth of fp32 operands into registers (8 rows x 32 bytes per thread)
-        auto load_stage = [&](int kt, float4 (&v)[16]) {
+        // gather one stage worth of fp32 operands into registers (4 rows x 32 bytes per thread)
+        auto load_stage = [&](int kt, float4 (&v)[8]) {
             const int tap = kt / kblocks;
             const int c = (kt - tap * kblocks) * kTileK + j * 8;
             const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 v[2 * i] = f4zero();
                 v[2 * i + 1] = f4zero();
                 if (oyx[i] >= 0 && c < p.Cin) {
@@ -228,15 +230,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             }
         };
         // split to bf16 hi/lo and publish the stage to the MMA warp
-        auto store_stage = [&](int kt, const float4 (&v)[16]) {
+        auto store_stage = [&](int kt, const float4 (&v)[8]) {
             const int s = kt % STAGES;
             const uint32_t ph = (kt / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* a_hi = smem + s * S::kStage;
             uint8_t* a_lo = a_hi + S::kA;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i * 16 + (t >> 3);
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 32 + (t >> 3);
                 uint4 hi, lo;
                 split8(v[2 * i], v[2 * i + 1], hi, lo);
                 const int off = r * 128 + ((j ^ (r & 7)) << 4);
@@ -247,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             mbar_arrive(&full_bar[s]);
         };
         // software pipeline: the loads of stage kt+1 are in flight while stage kt is converted and stored
-        float4 va[16], vb[16];
+        float4 va[8], vb[8];
         load_stage(0, va);
         for (int kt = 0; kt < KT; kt += 2) {
             if (kt + 1 < KT) load_stage(kt + 1, vb);
@@ -260,7 +262,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         // ---------------- epilogue ------------------------------------------------------------------
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int m = m0 + warp * 32 + lane;
+        const int quarter = warp & 3, half = warp >> 2;     // TMEM lane quarter, column half of this warp
+        const int m = m0 + quarter * 32 + lane;
         const bool row_ok = m < M;
         int b = 0;
         long long pix = 0;
@@ -270,10 +273,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         }
         const float rs = (MB && row_ok && p.row_scale) ? __ldg(p.row_scale + b) : 1.f;
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
+        for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
             if (n0 + cc * 32 >= p.Cout) break;           // warp-uniform: nothing left in this tile
             uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
             if (!row_ok) continue;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -302,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             }
         }
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ---------------- TMA: weight tiles (hi plane, lo plane) ---------------------------------------
         if (lane == 0) {
             for (int kt = 0; kt < KT; ++kt) {
@@ -342,7 +345,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc<BN>(tmem_base);
     }
@@ -743,7 +746,7 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
-        conv_tc_kernel<BN_, ST_, MB_><<<grid, kTcThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
+        conv_tc_kernel<BN_, ST_, MB_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
     } while (0)
 #define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
     do {                                                                                                                  \
