@@ -220,7 +220,7 @@ def run_ours(args):
     sampler.join(timeout=2)
 
     # per-kernel breakdown with CUDA events around every C-ABI launch (extra profiled steps, rank 0)
-    roofline, breakdown, cpu_base = None, None, None
+    roofline, breakdown, cpu_base, kroof = None, None, None, None
     if rank == 0:
         peaks = load_peaks()
         prof = _native.Profiler()
@@ -231,6 +231,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         _native.PROFILER = None
         table = prof.table()
+        kroof = prof.rooflines(peaks['hbm_gbs'], peaks['bf16_tflops_sustained'] or peaks['bf16_tflops'])
         tot = sum(v[0] for v in table.values())
         breakdown = {k: dict(ms_per_step=round(v[0] / psteps, 4), launches_per_step=v[1] // psteps,
                              share=round(v[0] / tot, 4)) for k, v in sorted(table.items(), key=lambda kv: -kv[1][0])[:(200 if args.full_breakdown else 12)]}
@@ -273,6 +274,7 @@ def run_ours(args):
                     e2e=dict(value=round(imgs / (ms_e2e * 1e-3), 2), unit='img/s',
                              h2d_bytes_per_step=images_h.numel() * 4 + ann_h.numel() * 4, d2h_bytes_per_step=4),
                     gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_base, kernel_breakdown=breakdown,
+                    kernel_rooflines=kroof if args.full_breakdown else None,
                     model_tflops=round(3 * FWD_GFLOP_PER_IMG * imgs / (ms * 1e-3) / 1e3, 2))
         print(json.dumps(line))
     if world > 1:

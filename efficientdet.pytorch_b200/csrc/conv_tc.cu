@@ -830,9 +830,10 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     const int BC = a->Cin > 64 ? 256 : 64;
     const int ctiles = cdiv(a->Cin, BC), ntiles = cdiv(a->Cout, kTileM);
     const int nchunks = g.nbx * g.nby * g.nbb;
-    int splits = cdiv(148 * 2, ctiles * ntiles * taps);
+    // split-K so that the grid is as close as possible to (but not above) two full waves of 148 CTAs
+    int splits = (148 * 2) / (ctiles * ntiles * taps);
     if (splits < 1) splits = 1;
-    if (splits > cdiv(nchunks, 8)) splits = cdiv(nchunks, 8);
+    if (splits > cdiv(nchunks, 4)) splits = cdiv(nchunks, 4);
     int cps = cdiv(nchunks, splits);
     splits = cdiv(nchunks, cps);
     dim3 grid(ctiles * ntiles, taps, splits);

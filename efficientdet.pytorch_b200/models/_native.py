@@ -185,9 +185,32 @@ class Profiler:
 
     def __init__(self):
         self.recs = []
+        self.work = []
 
-    def add(self, name, tag, e0, e1):
+    def add(self, name, tag, e0, e1, nbytes=0, flops=0):
         self.recs.append((name, tag, e0, e1))
+        self.work.append((nbytes, flops))
+
+    def rooflines(self, hbm_gbs, tensor_tflops):
+        """per entry-point class: device ms, algorithmic GB/s and TFLOP/s and the fraction of the measured peaks"""
+        out = {}
+        for (n, t, e0, e1), (nb, fl) in zip(self.recs, self.work):
+            key = n.replace('effdet_', '')
+            if t is not None:
+                key += ' k%d %d->%d' % (t[5], t[3], t[4])
+            v = out.setdefault(key, [0.0, 0, 0.0, 0.0])
+            v[0] += e0.elapsed_time(e1)
+            v[1] += 1
+            v[2] += nb
+            v[3] += fl
+        res = {}
+        for k, (ms, cnt, nb, fl) in out.items():
+            if ms <= 0:
+                continue
+            gbs, tfs = nb / ms / 1e6, fl / ms / 1e9
+            res[k] = dict(ms=round(ms, 4), launches=cnt, gb_per_s=round(gbs, 1), hbm_frac=round(gbs / hbm_gbs, 3),
+                          tflops=round(tfs, 2), tensor_frac=round(tfs / tensor_tflops, 4))
+        return res
 
     def _ms(self):
         return [(n, t, e0.elapsed_time(e1)) for (n, t, e0, e1) in self.recs]
@@ -213,8 +236,9 @@ class Profiler:
         return fl, ms_tot, n
 
 
-def call(name, dev_tensor, *args):
-    """Invoke an entry point on dev_tensor's device and the current stream of that device."""
+def call(name, dev_tensor, *args, nbytes=0, flops=0):
+    """Invoke an entry point on dev_tensor's device and the current stream of that device.
+    nbytes / flops: ALGORITHMIC work of this launch, only used by the bench profiler."""
     lib = load()
     dev = dev_tensor.device.index
     if dev is None:
@@ -231,6 +255,10 @@ def call(name, dev_tensor, *args):
         if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
             a = args[0]
             tag = (a.B, a.H, a.W, a.Cin, a.Cout, a.ksize)
-        prof.add(name, tag, e0, e1)
+        if tag is not None and not flops:
+            flops = 2.0 * tag[0] * tag[1] * tag[2] * tag[5] * tag[5] * tag[3] * tag[4]
+            if not nbytes:
+                nbytes = 4.0 * (tag[0] * tag[1] * tag[2] * (tag[3] + tag[4]) + tag[5] * tag[5] * tag[3] * tag[4])
+        prof.add(name, tag, e0, e1, nbytes, flops)
     if rc != 0:
         raise EffdetNativeError('%s failed (%d): %s' % (name, rc, last_error()))

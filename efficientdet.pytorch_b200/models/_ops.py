@@ -218,7 +218,7 @@ def bnact_bwd(dy, z, scale, shift, mean, rstd, act, row_scale=None, gate=None, d
     a = N.BnActBwdArgs(N.f32(dy, 'dy'), N.f32(z, 'z'), N.f32(dz), N.f32(scale), N.f32(shift), N.f32(mean, 'mean'),
                        N.f32(rstd), N.f32(dgamma), N.f32(dbeta), N.f32(row_scale), N.f32(gate), N.f32(dmean),
                        1.0 / HW, B, HW, C, act)
-    N.call('effdet_bnact_bwd', z, a)
+    N.call('effdet_bnact_bwd', z, a, nbytes=12.0 * z.numel())          # read dy, z; write dz
     return dz, dgamma, dbeta
 
 
@@ -252,7 +252,7 @@ class StemFn(torch.autograd.Function):
         y = _empty((B, Ho, Wo, C0), x)
         wc = _contig(w.detach())
         N.call('effdet_stem_fwd', x, N.f32(x, 'image'), N.f32(wc), N.f32(scale), N.f32(shift), N.f32(z), N.f32(y),
-               B, H, W, C0)
+               B, H, W, C0, nbytes=4.0 * (x.numel() + 2 * z.numel()))
         ctx.save_for_backward(x, z, scale, shift, rmean, rstd)
         ctx.C0 = C0
         return y
@@ -264,7 +264,8 @@ class StemFn(torch.autograd.Function):
         B, _, H, W = x.shape
         dz, dgamma, dbeta = bnact_bwd(dy, z, scale, shift, rmean, rstd, ACT_SWISH)
         dw = _zeros((ctx.C0, 3, 3, 3), x)
-        N.call('effdet_stem_wgrad', x, N.f32(x), N.f32(dz), N.f32(dw), B, H, W, ctx.C0)
+        N.call('effdet_stem_wgrad', x, N.f32(x), N.f32(dz), N.f32(dw), B, H, W, ctx.C0,
+               nbytes=4.0 * (x.numel() + dz.numel()))
         return None, dw, dgamma, dbeta, None, None, None
 
 
@@ -304,11 +305,12 @@ class MBConvFn(torch.autograd.Function):
         a1 = _empty((B, Ho, Wo, C), x)
         wkkc = pack_dw(Wd)
         N.call('effdet_dwconv_fwd', x, N.f32(a0), N.f32(wkkc), N.f32(sc1), N.f32(sh1), N.f32(z1), N.f32(a1),
-               B, H, W, C, k, s, pt, pl, Ho, Wo)
+               B, H, W, C, k, s, pt, pl, Ho, Wo, nbytes=4.0 * (a0.numel() + 2 * z1.numel()))
         # squeeze-excite
         S = Wr.shape[0]
         mean = _zeros((B, C), x)
-        N.call('effdet_spatial_reduce', x, N.f32(a1), None, N.f32(mean), 1.0 / (Ho * Wo), B, Ho * Wo, C)
+        N.call('effdet_spatial_reduce', x, N.f32(a1), None, N.f32(mean), 1.0 / (Ho * Wo), B, Ho * Wo, C,
+               nbytes=4.0 * a1.numel())
         s_pre = _empty((B, S), x)
         gate = _empty((B, C), x)
         wr, wx = _contig(Wr.detach()), _contig(Wx.detach())
@@ -349,7 +351,8 @@ class MBConvFn(torch.autograd.Function):
         dq = conv2d(dz2, wpd, C, 1, w_tc=tc_packs(Wp)[1])     # grad w.r.t. (a1 * gate)
         # squeeze-excite backward
         dgate = _zeros((B, C), x)
-        N.call('effdet_spatial_reduce', x, N.f32(dq), N.f32(a1), N.f32(dgate), 1.0, B, Ho * Wo, C)
+        N.call('effdet_spatial_reduce', x, N.f32(dq), N.f32(a1), N.f32(dgate), 1.0, B, Ho * Wo, C,
+               nbytes=8.0 * a1.numel())
         S = Wr.shape[0]
         dmean = _empty((B, C), x)
         dWr, dbr, dWx, dbx = torch.zeros_like(Wr), torch.zeros_like(br), torch.zeros_like(Wx), torch.zeros_like(bx)
@@ -362,10 +365,10 @@ class MBConvFn(torch.autograd.Function):
         a0 = t['a0']
         dWd = torch.zeros_like(Wd)
         N.call('effdet_dwconv_bwd_weight', x, N.f32(a0), N.f32(dz1), N.f32(dWd), B, H, W, C, k, s, cfg['pad_t'],
-               cfg['pad_l'], Ho, Wo)
+               cfg['pad_l'], Ho, Wo, nbytes=4.0 * (a0.numel() + dz1.numel()))
         da0 = _empty((B, H, W, C), x)
         N.call('effdet_dwconv_bwd_data', x, N.f32(dz1), N.f32(t['wkkc']), N.f32(da0), B, H, W, C, k, s,
-               cfg['pad_t'], cfg['pad_l'], Ho, Wo)
+               cfg['pad_t'], cfg['pad_l'], Ho, Wo, nbytes=4.0 * (dz1.numel() + da0.numel()))
         grads = []
         if cfg['expand']:
             We = P[0]
@@ -429,7 +432,8 @@ def _fuse_fwd(a, b, c, w, col, eps, mode):
     out = torch.empty_like(a)
     wst = w.shape[1]
     args = N.FuseArgs(N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(out), B, H, W, C, mode)
-    N.call('effdet_bifpn_fuse_fwd', a, args)
+    N.call('effdet_bifpn_fuse_fwd', a, args,
+           nbytes=4.0 * (2 * a.numel() + b.numel() + (c.numel() if c is not None else 0)))
     return out
 
 
@@ -440,7 +444,8 @@ def _fuse_bwd(dout, a, b, c, w, col, eps, mode, da, acc_a, db, acc_b, dc, acc_c,
     args = N.FuseBwdArgs(N.f32(dout), N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(da),
                          N.f32(db), N.f32(dc), acc_a, acc_b, acc_c, dw.data_ptr() + 4 * col, N.f32(scratch),
                          B, H, W, C, mode)
-    N.call('effdet_bifpn_fuse_bwd', a, args)
+    N.call('effdet_bifpn_fuse_bwd', a, args,
+           nbytes=4.0 * (3 * a.numel() + 2 * b.numel() + (2 * c.numel() if c is not None else 0)))
 
 
 class BiFPNLayerFn(torch.autograd.Function):
@@ -595,7 +600,8 @@ class RetinaHeadFn(torch.autograd.Function):
         F = cls_p[0].shape[0]
         dcls, dreg = _contig(dcls), _contig(dreg)
         dzc = torch.empty_like(dcls)
-        N.call('effdet_sigmoid_bwd', dcls, N.f32(dcls), N.f32(cls_all), N.f32(dzc), dcls.numel())
+        N.call('effdet_sigmoid_bwd', dcls, N.f32(dcls), N.f32(cls_all), N.f32(dzc), dcls.numel(),
+               nbytes=12.0 * dcls.numel())
         gP = [torch.zeros_like(p) for p in P]
         g_cls, g_reg = gP[:2 * stacked], gP[2 * stacked:4 * stacked]
         gwc, gbc, gwr, gbr = gP[4 * stacked:4 * stacked + 4]
@@ -651,7 +657,8 @@ class FocalLossFn(torch.autograd.Function):
         assign = torch.empty((B, A), device=cls.device, dtype=torch.int32)
         stats = _empty((B, 4), cls)
         N.call('effdet_focal_loss_fwd', cls, N.f32(cls), N.f32(reg), N.f32(anchors.view(-1, 4)), N.f32(annots),
-               N.f32(losses), assign.data_ptr(), N.f32(stats), B, A, K, G, float(alpha), float(gamma))
+               N.f32(losses), assign.data_ptr(), N.f32(stats), B, A, K, G, float(alpha), float(gamma),
+               nbytes=4.0 * (cls.numel() + reg.numel()))
         ctx.save_for_backward(cls, reg, anchors, annots, assign, stats)
         ctx.hp = (float(alpha), float(gamma))
         return losses.narrow(0, 0, 1), losses.narrow(0, 1, 1)
@@ -668,7 +675,8 @@ class FocalLossFn(torch.autograd.Function):
             gout[1:2].copy_(g_reg.reshape(1))
         dcls, dreg = torch.empty_like(cls), torch.empty_like(reg)
         N.call('effdet_focal_loss_bwd', cls, N.f32(cls), N.f32(reg), N.f32(anchors.view(-1, 4)), N.f32(annots),
-               N.f32(gout), assign.data_ptr(), N.f32(stats), N.f32(dcls), N.f32(dreg), B, A, K, G, ctx.hp[0], ctx.hp[1])
+               N.f32(gout), assign.data_ptr(), N.f32(stats), N.f32(dcls), N.f32(dreg), B, A, K, G, ctx.hp[0], ctx.hp[1],
+               nbytes=8.0 * (cls.numel() + reg.numel()))
         return dcls, dreg, None, None, None, None
 
 
