@@ -23,23 +23,37 @@ __global__ void __launch_bounds__(256) bnact_bwd_kernel(const effdet_bnact_bwd_a
         const float rowsc = p.row_scale ? __ldg(p.row_scale + b) : 1.f;
         const int r_begin = blockIdx.x * rows_per_block;
         const int r_end = min(p.HW, r_begin + rows_per_block);
-        for (int r = r_begin + rp.tr; r < r_end; r += rp.rows) {
-            const long long off = ((long long)b * p.HW + r) * p.C + c;
-            float4 g = ldg4(p.dy + off);
-            const float4 zz = ldg4(p.z + off);
-            if (p.gate) g = f4fma(g, gt, dm);
-            g = f4scale(g, rowsc);
-            float4 du = g;
-            if (p.act == EFFDET_ACT_SWISH) {
-                const float4 u = f4fma(zz, sc, sh);
-                du = make_float4(g.x * swish_gradf_(u.x), g.y * swish_gradf_(u.y), g.z * swish_gradf_(u.z),
-                                 g.w * swish_gradf_(u.w));
+        // 4 rows per trip: 8 independent 128-bit loads in flight per thread before any arithmetic
+        constexpr int U = 4;
+        for (int r0 = r_begin + rp.tr; r0 < r_end; r0 += U * rp.rows) {
+            float4 gv[U], zv[U];
+            long long offs[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + u * rp.rows;
+                offs[u] = ((long long)b * p.HW + (r < r_end ? r : r0)) * p.C + c;
+                gv[u] = ldg4(p.dy + offs[u]);
+                zv[u] = ldg4(p.z + offs[u]);
             }
-            const float4 xh = make_float4((zz.x - mu.x) * rs.x, (zz.y - mu.y) * rs.y, (zz.z - mu.z) * rs.z,
-                                          (zz.w - mu.w) * rs.w);
-            sg = f4fma(du, xh, sg);
-            sb = f4add(sb, du);
-            st4(p.dz + off, f4mul(du, sc));
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r0 + u * rp.rows >= r_end) break;
+                float4 g = gv[u];
+                const float4 zz = zv[u];
+                if (p.gate) g = f4fma(g, gt, dm);
+                g = f4scale(g, rowsc);
+                float4 du = g;
+                if (p.act == EFFDET_ACT_SWISH) {
+                    const float4 u4 = f4fma(zz, sc, sh);
+                    du = make_float4(g.x * swish_gradf_(u4.x), g.y * swish_gradf_(u4.y), g.z * swish_gradf_(u4.z),
+                                     g.w * swish_gradf_(u4.w));
+                }
+                const float4 xh = make_float4((zz.x - mu.x) * rs.x, (zz.y - mu.y) * rs.y, (zz.z - mu.z) * rs.z,
+                                              (zz.w - mu.w) * rs.w);
+                sg = f4fma(du, xh, sg);
+                sb = f4add(sb, du);
+                st4(p.dz + offs[u], f4mul(du, sc));
+            }
         }
     }
     red_g[threadIdx.x] = sg;

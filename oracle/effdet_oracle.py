@@ -164,8 +164,8 @@ def state_dict_spec(cfg):
 # per-layer-kind gains of the 'wellcond' weight set: chosen so every intermediate of D0..D7
 # stays O(1) (measured: stage outputs 0.5-3, neck 0.5-3, logits std ~1.5 around the prior bias)
 _WELLCOND_GAIN = {'default': 1.0, '_conv_stem': 1.5, '_expand_conv': 1.6, '_depthwise_conv': 1.6,
-                  '_project_conv': 1.1, '_se_reduce': 1.0, '_se_expand': 1.0, 'lateral_convs': 1.4,
-                  'bifpn_convs': 1.3, 'cls_convs': 1.45, 'reg_convs': 1.45, 'retina_cls': 1.0,
+                  '_project_conv': 1.1, '_project_skip': 0.45, '_se_reduce': 1.0, '_se_expand': 1.0, 'lateral_convs': 1.4,
+                  'bifpn_convs': 1.22, 'cls_convs': 1.45, 'reg_convs': 1.45, 'retina_cls': 1.5,
                   'retina_reg': 0.5}
 
 
@@ -213,6 +213,11 @@ def init_state_dict(cfg, seed=0, mode='wellcond'):
                 for key, gval in _WELLCOND_GAIN.items():
                     if key in name:
                         gain = gval
+                if '_project_conv' in name:
+                    # residual (repeat) blocks get a damped branch so deep stages (D4..D7) do not blow up
+                    bi = int(name.split('_blocks.')[1].split('.')[0])
+                    if cfg['blocks'][bi]['skip']:
+                        gain = _WELLCOND_GAIN['_project_skip']
                 t = randn(shape, gain / math.sqrt(fan_in))
             elif kind == 'bn_w':
                 t = rand(shape, 0.7, 1.3)

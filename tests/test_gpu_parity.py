@@ -538,3 +538,69 @@ def test_model_train_step_vs_reference_golden(tag, prec):
     print(tag, prec, 'worst grad rel err', worst)
     for k in ('backbone._conv_head.weight', 'backbone._bn1.weight', 'backbone._fc.weight'):
         assert params[k].grad is None
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] / configs[4]: the larger family members as parity cases (oracle on the host)
+# ------------------------------------------------------------------------------------------------
+
+def test_d4_1024_train_step_vs_oracle():
+    """EfficientDet-D4 geometry (B4 backbone, W_bifpn 224, D_bifpn 6 per utils/config_eff.py, 1024x1024):
+    one forward+backward, losses and a spread of parameter gradients against the CPU oracle."""
+    cfg = O.make_config('efficientdet-d4', num_classes=20, W_bifpn=224, D_bifpn=6)
+    sd = O.init_state_dict(cfg, seed=41)
+    m = _build('efficientdet-d4', 20, 224, 6, sd, is_training=True)
+    m.eval()
+    m.is_training = True
+    images, ann = O.synthetic_batch(1, size=1024, num_classes=20, seed=42)
+    cl, rl = m([images.to(_dev()), ann.to(_dev())])
+    (cl.mean() + rl.mean()).backward()
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sdg = _grad_sd(sd)
+    ocl, orl = O.train_forward(sdg, images, ann, cfg)
+    (ocl.mean() + orl.mean()).backward()
+    assert _rel(cl.detach().cpu(), ocl.detach()) < TOL and _rel(rl.detach().cpu(), orl.detach()) < TOL
+    params = dict(m.named_parameters())
+    worst = (0.0, None)
+    for k, p in params.items():
+        ref = sdg[k].grad
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        e = _rel(p.grad.cpu(), ref)
+        if e > worst[0]:
+            worst = (e, k)
+    print('d4 1024 losses', float(cl), float(rl), 'worst grad rel err', worst)
+    assert worst[0] < TOL_GRAD['bf16x3']
+
+
+def test_d7_1536_inference_vs_oracle():
+    """EfficientDet-D7 geometry (B6 backbone, W_bifpn 384, D_bifpn 8, 1536x1536, 441 936 anchors):
+    forward + decode + NMS on the device against the CPU oracle."""
+    cfg = O.make_config('efficientdet-d7', num_classes=20, W_bifpn=384, D_bifpn=8)
+    sd = O.init_state_dict(cfg, seed=51)
+    m = _build('efficientdet-d7', 20, 384, 8, sd, is_training=False)
+    m.eval()
+    images, _ = O.synthetic_batch(1, size=1536, seed=52)
+    x = images.to(_dev())
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    with torch.no_grad():
+        ocls, oreg, _ = O.raw_outputs(sd, images, cfg)
+    # eval.py:349-352 uses 0.4; with random weights pick the score of the ~6000th best anchor instead so the
+    # (quadratic, numpy) oracle NMS stays affordable -- both sides get the same threshold
+    thr = float(torch.sort(ocls.max(dim=2)[0].flatten(), descending=True)[0][6000])
+    thr = max(thr, 0.05)
+    m.threshold, m.iou_threshold = thr, 0.5
+    with torch.no_grad():
+        feats = m.extract_feat(x)
+        cls_l, reg_l = m.bbox_head(feats)
+        det = m(x)
+    coll = {}
+    with torch.no_grad():
+        ref = O.detect(sd, images, cfg, threshold=thr, iou_threshold=0.5, collect=coll)
+    cls, reg = torch.cat(cls_l, dim=1), torch.cat(reg_l, dim=1)
+    assert cls.shape[1] == 441936
+    e_c, e_r = _rel(cls.cpu(), coll['cls']), _rel(reg.cpu(), coll['reg'])
+    print('d7 1536: cls rel %.2e reg rel %.2e, detections ours %d oracle %d' % (e_c, e_r, det[0].numel(), ref[0].numel()))
+    assert e_c < TOL and e_r < TOL
+    n_ref = ref[0].numel()
+    assert abs(det[0].numel() - n_ref) <= max(3, n_ref // 25)
