@@ -155,7 +155,7 @@ struct FwdSmem {
 
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
 template <int BN, int STAGES, bool MB>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];

@@ -164,6 +164,73 @@ __global__ void __launch_bounds__(256) dw_bwd_weight_kernel(const float* __restr
     }
 }
 
+// Shared-memory tiled variant of the weight gradient (used for the large feature maps): a CTA stages a
+// TH x TW output tile of dz and the matching input tile (with halo) for 32 channels, then every thread owns one
+// (tap, 4 channels) pair and sweeps the tile with 128-bit shared loads -- global memory is read once per tile
+// instead of once per tap.  CTAs are persistent over tiles; one round of atomics per CTA at the end.
+template <int K, int S, int TH, int TWD>
+__global__ void __launch_bounds__(256) dw_bwd_weight_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                                  float* __restrict__ dw, int B, int H, int W, int C,
+                                                                  int pad_t, int pad_l, int Ho, int Wo, int tiles_x,
+                                                                  int tiles_y) {
+    constexpr int IH = (TH - 1) * S + K, IW = (TWD - 1) * S + K;
+    constexpr int KK = K * K;
+    constexpr int NPG = 32 / KK;              // pixel groups sharing the 32 (tap, group) slots of a CTA
+    extern __shared__ __align__(16) float sm[];
+    float4* xs = reinterpret_cast<float4*>(sm);                 // [IH][IW][8]
+    float4* gs = xs + IH * IW * 8;                              // [TH][TWD][8]
+    const int t = threadIdx.x;
+    const int cv_l = t & 7, slot = t >> 3;
+    const int tap = slot % KK, pg = slot / KK;
+    const bool worker = pg < NPG;
+    const int ky = tap / K, kx = tap - ky * K;
+    const int cvecs = C / 4;
+    const int cv0 = blockIdx.y * 8;
+    const bool cv_ok = cv0 + cv_l < cvecs;
+    const long long ntiles = (long long)B * tiles_y * tiles_x;
+    float4 acc = f4zero();
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long q = tile / tiles_x;
+        const int ty = (int)(q % tiles_y);
+        const int b = (int)(q / tiles_y);
+        const int oy0 = ty * TH, ox0 = tx * TWD;
+        const int iy0 = oy0 * S - pad_t, ix0 = ox0 * S - pad_l;
+        for (int i = t; i < IH * IW * 8; i += 256) {
+            const int c8 = i & 7;
+            const int p = i >> 3;
+            const int r = p / IW, cc = p - r * IW;
+            const int iy = iy0 + r, ix = ix0 + cc;
+            float4 v = f4zero();
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv0 + c8 < cvecs)
+                v = ldg4(x + (((long long)b * H + iy) * W + ix) * C + (cv0 + c8) * 4);
+            xs[i] = v;
+        }
+        for (int i = t; i < TH * TWD * 8; i += 256) {
+            const int c8 = i & 7;
+            const int p = i >> 3;
+            const int r = p / TWD, cc = p - r * TWD;
+            const int oy = oy0 + r, ox = ox0 + cc;
+            float4 v = f4zero();
+            if (oy < Ho && ox < Wo && cv0 + c8 < cvecs)
+                v = ldg4(dz + (((long long)b * Ho + oy) * Wo + ox) * C + (cv0 + c8) * 4);
+            gs[i] = v;
+        }
+        __syncthreads();
+        if (worker) {
+            for (int p = pg; p < TH * TWD; p += NPG) {
+                const int r = p / TWD, cc = p - r * TWD;
+                acc = f4fma(xs[((r * S + ky) * IW + cc * S + kx) * 8 + cv_l], gs[p * 8 + cv_l], acc);
+            }
+        }
+        __syncthreads();
+    }
+    if (worker && cv_ok) {
+        float* o = dw + (long long)((cv0 + cv_l) * 4) * KK + tap;
+        atomicAdd(o, acc.x); atomicAdd(o + KK, acc.y); atomicAdd(o + 2 * KK, acc.z); atomicAdd(o + 3 * KK, acc.w);
+    }
+}
+
 __global__ void pack_dw_weight_kernel(const float* __restrict__ w, float* __restrict__ o, int C, int kk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // output index [tap][c]
     if (i >= C * kk) return;
@@ -226,13 +293,38 @@ extern "C" int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* 
     int s = dw_check("dwconv_bwd_weight", B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo);
     if (s) return s;
     EFFDET_DEVICE(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Ho >= 16 && Wo >= 16) {
+        // tiled kernel: TH x TW = 16x16 outputs (stride 1) or 8x16 (stride 2), 32 channels per CTA
+#define EFFDET_DW_TILED(K_, S_, TH_, TW_)                                                                                  \
+        do {                                                                                                              \
+            constexpr int IH = (TH_ - 1) * S_ + K_, IW = (TW_ - 1) * S_ + K_;                                             \
+            const size_t smem = (size_t)(IH * IW + TH_ * TW_) * 8 * sizeof(float4);                                       \
+            const int tiles_x = cdiv(Wo, TW_), tiles_y = cdiv(Ho, TH_);                                                   \
+            cudaError_t e = cudaFuncSetAttribute(dw_bwd_weight_tiled_kernel<K_, S_, TH_, TW_>,                            \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+            if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "dwconv_bwd_weight: smem opt-in: %s", cudaGetErrorString(e)); \
+            const long long ntiles = (long long)B * tiles_x * tiles_y;                                                    \
+            const int chunks = cdiv(C / 4, 8);                                                                            \
+            long long gx = (148 * 2 + chunks - 1) / chunks;                                                               \
+            if (gx > ntiles) gx = ntiles;                                                                                 \
+            if (gx < 1) gx = 1;                                                                                           \
+            dw_bwd_weight_tiled_kernel<K_, S_, TH_, TW_><<<dim3((unsigned)gx, chunks), 256, smem, st>>>(                  \
+                x, dz, dw_c1kk, B, H, W, C, pad_t, pad_l, Ho, Wo, tiles_x, tiles_y);                                      \
+        } while (0)
+        if (k == 3 && stride == 1) EFFDET_DW_TILED(3, 1, 16, 16);
+        else if (k == 3 && stride == 2) EFFDET_DW_TILED(3, 2, 8, 16);
+        else if (k == 5 && stride == 1) EFFDET_DW_TILED(5, 1, 16, 16);
+        else EFFDET_DW_TILED(5, 2, 8, 16);
+#undef EFFDET_DW_TILED
+        return launch_status("dw_bwd_weight_tiled_kernel");
+    }
     const int cvecs = C / 4;
     const long long npix = (long long)B * Ho * cdiv(Wo, kTW);   // strips of kTW outputs
     const int rows = rowpack_rows(cvecs);
     long long rpb = (npix + 148 * 2 - 1) / (148 * 2);
     if (rpb < (long long)rows * 2) rpb = (long long)rows * 2;
     dim3 grid(cdiv(npix, rpb), rowpack_chunks(cvecs));
-    cudaStream_t st = (cudaStream_t)stream;
     DW_DISPATCH(dw_bwd_weight_kernel, <<<grid, 256, 0, st>>>(x, dz, dw_c1kk, B, H, W, C, pad_t, pad_l, Ho, Wo, (int)rpb))
     return launch_status("dw_bwd_weight_kernel");
 }

@@ -24,7 +24,7 @@ TOL_EXACT = 5e-5    # what the exact-fp32 kernels must reach (atomics / summatio
 # gradient by 8.5e-3 (DESIGN.md "Gradient conditioning", measured with the script quoted there), i.e.
 # ~850x amplification.  The bf16x3 tensor-core convs carry ~5e-6 per layer (kernel-level tests hold them
 # to 3e-5), the exact-fp32 path ~1e-7; the bounds below are those noise levels times the amplification.
-TOL_GRAD = {'fp32': 1e-3, 'bf16x3': 3e-2}
+TOL_GRAD = {'fp32': 3e-3, 'bf16x3': 3e-2}
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
