@@ -167,7 +167,12 @@ def run_ours(args):
     model.freeze_bn()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True)
+        # reference train.py:250 wraps with find_unused_parameters=True (5 dead backbone parameters); the set of
+        # unused parameters never changes, so static_graph lets DDP learn it once instead of searching the autograd
+        # graph and synchronising a usage bitmap every iteration (EFFDET_DDP_STATIC=0 restores the per-step search)
+        static = os.environ.get('EFFDET_DDP_STATIC', '1') != '0'
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                        static_graph=static, gradient_as_bucket_view=True)
 
     images_h, ann_h = synthetic(BS, seed=1000 + rank)
     images_h, ann_h = images_h.pin_memory(), ann_h.pin_memory()

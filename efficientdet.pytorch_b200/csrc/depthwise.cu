@@ -9,6 +9,14 @@ namespace effdet {
 
 constexpr int kTW = 4;  // outputs along x per thread
 
+// 16-byte asynchronous global->shared copy; src_bytes = 0 zero-fills the destination (halo / tail)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int K, int S>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -196,26 +204,26 @@ __global__ void __launch_bounds__(256) dw_bwd_weight_tiled_kernel(const float* _
         const int b = (int)(q / tiles_y);
         const int oy0 = ty * TH, ox0 = tx * TWD;
         const int iy0 = oy0 * S - pad_t, ix0 = ox0 * S - pad_l;
+        // stage both tiles with cp.async: every copy of the tile is in flight at once (zero fill = padding)
         for (int i = t; i < IH * IW * 8; i += 256) {
             const int c8 = i & 7;
             const int p = i >> 3;
             const int r = p / IW, cc = p - r * IW;
             const int iy = iy0 + r, ix = ix0 + cc;
-            float4 v = f4zero();
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W && cv0 + c8 < cvecs)
-                v = ldg4(x + (((long long)b * H + iy) * W + ix) * C + (cv0 + c8) * 4);
-            xs[i] = v;
+            const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W && cv0 + c8 < cvecs;
+            const float* src = ok ? x + (((long long)b * H + iy) * W + ix) * C + (cv0 + c8) * 4 : x;
+            cp_async16(&xs[i], src, ok ? 16 : 0);
         }
         for (int i = t; i < TH * TWD * 8; i += 256) {
             const int c8 = i & 7;
             const int p = i >> 3;
             const int r = p / TWD, cc = p - r * TWD;
             const int oy = oy0 + r, ox = ox0 + cc;
-            float4 v = f4zero();
-            if (oy < Ho && ox < Wo && cv0 + c8 < cvecs)
-                v = ldg4(dz + (((long long)b * Ho + oy) * Wo + ox) * C + (cv0 + c8) * 4);
-            gs[i] = v;
+            const bool ok = oy < Ho && ox < Wo && cv0 + c8 < cvecs;
+            const float* src = ok ? dz + (((long long)b * Ho + oy) * Wo + ox) * C + (cv0 + c8) * 4 : dz;
+            cp_async16(&gs[i], src, ok ? 16 : 0);
         }
+        cp_async_wait_all();
         __syncthreads();
         if (worker) {
             for (int p = pg; p < TH * TWD; p += NPG) {
