@@ -214,6 +214,13 @@ def run_ours(args):
     ms = timed(lambda: step(images_d, ann_d), args.steps)
     launches = _native.launch_count() // max(args.steps, 1)
 
+    # host-side issue time of one step (queue empty before, no sync after): how far the CPU runs ahead of the GPU
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    step(images_d, ann_d)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+
     # end-to-end: pinned host inputs -> H2D copy -> step -> loss read back, every step
     def e2e_step():
         x = images_h.to(dev, non_blocking=True)
@@ -279,7 +286,7 @@ def run_ours(args):
                     clocks=sampler.summary(),
                     e2e=dict(value=round(imgs / (ms_e2e * 1e-3), 2), unit='img/s',
                              h2d_bytes_per_step=images_h.numel() * 4 + ann_h.numel() * 4, d2h_bytes_per_step=4),
-                    gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_base, kernel_breakdown=breakdown,
+                    gpu_launches=launches, host_issue_ms_per_step=round(host_ms, 2), roofline=roofline, cpu_baseline=cpu_base, kernel_breakdown=breakdown,
                     kernel_rooflines=kroof if args.full_breakdown else None,
                     model_tflops=round(3 * FWD_GFLOP_PER_IMG * imgs / (ms * 1e-3) / 1e3, 2))
         print(json.dumps(line))
