@@ -106,6 +106,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// same load without the wait: lets the caller put independent global loads in flight first
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for the TMEM load and pin the registers after the wait (no use may be scheduled above it)
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile(""
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
 
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 "version 1" (cute::UMMA::SmemDescriptor):
 //   bits [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
@@ -150,7 +174,8 @@ struct FwdSmem {
     static constexpr int kA = kTileM * 128;   // bytes of one bf16 plane of the A tile
     static constexpr int kB = BN * 128;       // bytes of one bf16 plane of the B tile
     static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kChan = 3 * BN * 4;  // bias | scale | shift of this CTA's output channels
+    static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kChan;
 };
 
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
@@ -164,11 +189,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [3][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BN;
     const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
     const int KT = taps * kblocks;
+    for (int i = threadIdx.x; i < BN; i += kFwdThreads) {
+        const int n = n0 + i;
+        const bool ok = n < p.Cout;
+        chan[i] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+        chan[BN + i] = (MB && ok && p.scale) ? __ldg(p.scale + n) : 1.f;
+        chan[2 * BN + i] = (MB && ok && p.shift) ? __ldg(p.shift + n) : 0.f;
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -272,21 +305,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             pix = m - b * HW;
         }
         const float rs = (MB && row_ok && p.row_scale) ? __ldg(p.row_scale + b) : 1.f;
+        const int ncols = min(BN, p.Cout - n0);
+        const int nchunks = (ncols + 31) >> 5;
+        const int c_begin = half ? (nchunks + 1) >> 1 : 0, c_end = half ? nchunks : (nchunks + 1) >> 1;
+        const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
+        const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
+        const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
 #pragma unroll 1
-        for (int cc = half * (BN / 64); cc < (half + 1) * (BN / 64); ++cc) {
-            if (n0 + cc * 32 >= p.Cout) break;           // warp-uniform: nothing left in this tile
+        for (int cc = c_begin; cc < c_end; ++cc) {
             uint32_t acc[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
-            if (!row_ok) continue;
+            tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
+            // streaming operands of the epilogue go in flight while the TMEM load completes
+            float4 rv[8], mv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int n = n0 + cc * 32 + q * 4;
+                rv[q] = f4zero();
+                mv[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (row_ok && n < p.Cout) {
+                    if (p.residual) rv[q] = ldg4(p.residual + rbase + n);
+                    if (p.mask_src) mv[q] = ldg4(p.mask_src + mbase + n);
+                }
+            }
+            tmem_ld32_wait(acc);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int nl = cc * 32 + q * 4;
+                const int n = n0 + nl;
                 if (n >= p.Cout) break;
                 float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
                                        __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
-                if (p.bias) v = f4add(v, ldg4(p.bias + n));
-                if (MB && p.z) st4(p.z + (long long)b * p.y_bstride + pix * p.Cout + n, v);
-                if (MB && p.scale) v = f4fma(v, ldg4(p.scale + n), ldg4(p.shift + n));
+                v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
+                if (MB && p.z) st4(p.z + ybase + n, v);
+                if (MB) v = f4fma(v, *reinterpret_cast<const float4*>(chan + BN + nl), *reinterpret_cast<const float4*>(chan + 2 * BN + nl));
                 if (p.act == EFFDET_ACT_RELU) {
                     v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
                 } else if (p.act == EFFDET_ACT_SIGMOID) {
@@ -295,13 +347,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                     v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
                 }
                 if (MB && p.row_scale) v = f4scale(v, rs);
-                if (p.residual) v = f4add(v, ldg4(p.residual + (long long)b * p.r_bstride + pix * p.Cout + n));
-                if (p.mask_src) {
-                    const float4 g = ldg4(p.mask_src + (long long)b * p.m_bstride + pix * p.Cout + n);
-                    v = make_float4(g.x > 0.f ? v.x : 0.f, g.y > 0.f ? v.y : 0.f, g.z > 0.f ? v.z : 0.f,
-                                    g.w > 0.f ? v.w : 0.f);
-                }
-                st4(p.y + (long long)b * p.y_bstride + pix * p.Cout + n, v);
+                v = f4add(v, rv[q]);
+                if (p.mask_src)
+                    v = make_float4(mv[q].x > 0.f ? v.x : 0.f, mv[q].y > 0.f ? v.y : 0.f, mv[q].z > 0.f ? v.z : 0.f,
+                                    mv[q].w > 0.f ? v.w : 0.f);
+                st4(p.y + ybase + n, v);
             }
         }
         tc_fence_before();
