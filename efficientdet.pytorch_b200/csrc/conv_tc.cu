@@ -181,8 +181,7 @@ struct FwdSmem {
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
 template <int BN, int STAGES, bool MB>
 __global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
-conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks,
-               const int num_m_tiles) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -193,10 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
     float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [3][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;
-    // CTAs are persistent over M tiles (tile = blockIdx.x, blockIdx.x + gridDim.x, ...): the smem/TMEM/barrier
-    // setup is paid once, and when the whole reduction fits the pipeline (KT == STAGES) the weights stay resident
-    const bool stationary = (p.ksize * p.ksize * kblocks == STAGES);
+    const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BN;
     const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
     const int KT = taps * kblocks;
     for (int i = threadIdx.x; i < BN; i += kFwdThreads) {
@@ -225,11 +221,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         // ---------------- producers: im2col gather + bf16 split -----------------------------------
         const int t = threadIdx.x;
         const int j = t & 7;                 // 16-byte chunk (8 channels) within the 64-channel row
-        const int quarter = warp & 3, half = warp >> 2;     // TMEM lane quarter, column half of this warp
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x, ++it) {
-        const int m0 = tile * kTileM;
-        const int g0 = it * KT;              // running stage counter at the start of this tile
         long long base[4];
         int oyx[4];
 #pragma unroll
@@ -273,8 +264,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         };
         // split to bf16 hi/lo and publish the stage to the MMA warp
         auto store_stage = [&](int kt, const float4 (&v)[8]) {
-            const int s = (g0 + kt) % STAGES;
-            const uint32_t ph = ((g0 + kt) / STAGES) & 1;
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* a_hi = smem + s * S::kStage;
             uint8_t* a_lo = a_hi + S::kA;
@@ -302,8 +293,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
             }
         }
         // ---------------- epilogue ------------------------------------------------------------------
-        mbar_wait(accum_bar, it & 1);
+        mbar_wait(accum_bar, 0);
         tc_fence_after();
+        const int quarter = warp & 3, half = warp >> 2;     // TMEM lane quarter, column half of this warp
         const int m = m0 + quarter * 32 + lane;
         const bool row_ok = m < M;
         int b = 0;
@@ -362,37 +354,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 st4(p.y + ybase + n, v);
             }
         }
-        tc_fence_before();       // order this tile's TMEM reads before the next tile's MMAs (via the full barrier)
-        }                        // tile loop
+        tc_fence_before();
     } else if (warp == 8) {
         // ---------------- TMA: weight tiles (hi plane, lo plane) ---------------------------------------
         if (lane == 0) {
-            int g = 0;
-            for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
-                for (int kt = 0; kt < KT; ++kt, ++g) {
-                    const int s = g % STAGES;
-                    const uint32_t ph = (g / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (stationary && g >= KT) {
-                        mbar_arrive(&full_bar[s]);          // weights of this k-block are already resident
-                    } else {
-                        uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
-                        mbar_arrive_expect_tx(&full_bar[s], 2 * S::kB);
-                        tma_load_3d(b_hi, &wmap, &full_bar[s], kt * kTileK, n0, 0);
-                        tma_load_3d(b_hi + S::kB, &wmap, &full_bar[s], kt * kTileK, n0, 1);
-                    }
-                }
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
+                mbar_arrive_expect_tx(&full_bar[s], 2 * S::kB);
+                tma_load_3d(b_hi, &wmap, &full_bar[s], kt * kTileK, n0, 0);
+                tma_load_3d(b_hi + S::kB, &wmap, &full_bar[s], kt * kTileK, n0, 1);
             }
         }
     } else {
         // ---------------- MMA issue ----------------------------------------------------------------------
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kTileM, BN, 0, 0);
-            int g = 0;
-            for (int tile = blockIdx.x; tile < num_m_tiles; tile += gridDim.x) {
-            for (int kt = 0; kt < KT; ++kt, ++g) {
-                const int s = g % STAGES;
-                const uint32_t ph = (g / STAGES) & 1;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * S::kStage);
@@ -410,7 +392,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(accum_bar);
-            }                    // tile loop
         }
     }
     __syncthreads();
@@ -808,23 +789,14 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
-    const int num_m_tiles = cdiv(M, kTileM);
-    const int n_tiles = cdiv(a->Cout, BN);
-    // short reductions: ~2 resident CTAs per SM, each looping over many M tiles (setup amortised, weights
-    // stationary when KT == 1); long reductions: one CTA per tile as before
-    int gx = num_m_tiles;
-    if (KT <= 2) {
-        const int want = (148 * 2 + n_tiles - 1) / n_tiles;
-        if (num_m_tiles >= 4 * want) gx = want;
-    }
-    dim3 grid(gx, n_tiles);
+    dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
     const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
 #define EFFDET_TC_LAUNCH1(BN_, ST_, MB_)                                                                                   \
     do {                                                                                                                  \
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
-        conv_tc_kernel<BN_, ST_, MB_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks, num_m_tiles);      \
+        conv_tc_kernel<BN_, ST_, MB_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
     } while (0)
 #define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
     do {                                                                                                                  \
