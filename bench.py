@@ -172,7 +172,9 @@ def run_ours(args):
         # graph and synchronising a usage bitmap every iteration (EFFDET_DDP_STATIC=0 restores the per-step search)
         static = os.environ.get('EFFDET_DDP_STATIC', '1') != '0'
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
-                                                        static_graph=static, gradient_as_bucket_view=True)
+                                                        static_graph=static, gradient_as_bucket_view=True,
+                                                        # BN statistics are frozen (freeze_bn): nothing to re-broadcast per step
+                                                        broadcast_buffers=os.environ.get('EFFDET_DDP_BCAST', '0') == '1')
 
     images_h, ann_h = synthetic(BS, seed=1000 + rank)
     images_h, ann_h = images_h.pin_memory(), ann_h.pin_memory()
