@@ -72,6 +72,18 @@ def _zeros(shape, like):
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
 
+def _zeros_like_many(tensors):
+    """Zero-initialised gradient buffers for `tensors` carved out of ONE allocation / ONE memset (each
+    slice 16-byte aligned) instead of one fill kernel per parameter."""
+    sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
+    flat = torch.zeros((sum(sizes),), device=tensors[0].device, dtype=torch.float32)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # parameter-derived caches (invalidated by in-place updates: optimizer.step, load_state_dict)
 # ------------------------------------------------------------------------------------------------
@@ -345,7 +357,8 @@ class MBConvFn(torch.autograd.Function):
         # project BN (no activation), drop-connect scale folded in
         dz2, dg2, db2 = bnact_bwd(dy, t['z2'], t['sc2'], t['sh2'], t['rm2'], t['rs2'], ACT_NONE,
                                   row_scale=t['row_scale'])
-        dWp = torch.zeros_like(Wp)
+        zb = _zeros_like_many([Wp, Wr, br, Wx, bx, Wd] + ([P[0]] if cfg['expand'] else []))
+        dWp = zb[0]
         conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate, tc=tc_enabled())
         _, wpd = pack_conv(Wp)
         dq = conv2d(dz2, wpd, C, 1, w_tc=tc_packs(Wp)[1])     # grad w.r.t. (a1 * gate)
@@ -355,7 +368,7 @@ class MBConvFn(torch.autograd.Function):
                nbytes=8.0 * a1.numel())
         S = Wr.shape[0]
         dmean = _empty((B, C), x)
-        dWr, dbr, dWx, dbx = torch.zeros_like(Wr), torch.zeros_like(br), torch.zeros_like(Wx), torch.zeros_like(bx)
+        dWr, dbr, dWx, dbx = zb[1], zb[2], zb[3], zb[4]
         N.call('effdet_se_gate_bwd', x, N.f32(dgate), N.f32(t['mean']), N.f32(t['s_pre']), N.f32(gate),
                N.f32(_contig(Wr.detach())), N.f32(_contig(Wx.detach())), N.f32(dmean), N.f32(dWr), N.f32(dbr),
                N.f32(dWx), N.f32(dbx), B, C, S)
@@ -363,7 +376,7 @@ class MBConvFn(torch.autograd.Function):
         dz1, dg1, db1 = bnact_bwd(dq, t['z1'], t['sc1'], t['sh1'], t['rm1'], t['rs1'], ACT_SWISH, gate=gate,
                                   dmean=dmean)
         a0 = t['a0']
-        dWd = torch.zeros_like(Wd)
+        dWd = zb[5]
         N.call('effdet_dwconv_bwd_weight', x, N.f32(a0), N.f32(dz1), N.f32(dWd), B, H, W, C, k, s, cfg['pad_t'],
                cfg['pad_l'], Ho, Wo, nbytes=4.0 * (a0.numel() + dz1.numel()))
         da0 = _empty((B, H, W, C), x)
@@ -373,7 +386,7 @@ class MBConvFn(torch.autograd.Function):
         if cfg['expand']:
             We = P[0]
             dz0, dg0, db0 = bnact_bwd(da0, t['z0'], t['sc0'], t['sh0'], t['rm0'], t['rs0'], ACT_SWISH)
-            dWe = torch.zeros_like(We)
+            dWe = zb[6]
             conv_wgrad(x, dz0, dWe, None, 1, tc=tc_enabled())
             _, wed = pack_conv(We)
             dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
@@ -492,12 +505,13 @@ class BiFPNLayerFn(torch.autograd.Function):
         ins, td, out, fused, w1, w2, w1c, w2c, convs = ctx.keep
         douts = [_contig(d) for d in douts]
         C = ins[0].shape[3]
-        dw1, dw2 = torch.zeros_like(w1c), torch.zeros_like(w2c)
+        zb = _zeros_like_many([w1c, w2c] + list(convs))
+        dw1, dw2 = zb[0], zb[1]
         dconv = [None] * len(convs)
 
         def conv_bwd(idx, dy):
             w, b = convs[2 * idx], convs[2 * idx + 1]
-            dw, db = torch.zeros_like(w), torch.zeros_like(b)
+            dw, db = zb[2 + 2 * idx], zb[3 + 2 * idx]
             conv_wgrad(fused[idx], dy, dw, db, 3, tc=tc_enabled())
             dconv[2 * idx], dconv[2 * idx + 1] = dw, db
             _, wd = pack_conv(w)
@@ -602,7 +616,7 @@ class RetinaHeadFn(torch.autograd.Function):
         dzc = torch.empty_like(dcls)
         N.call('effdet_sigmoid_bwd', dcls, N.f32(dcls), N.f32(cls_all), N.f32(dzc), dcls.numel(),
                nbytes=12.0 * dcls.numel())
-        gP = [torch.zeros_like(p) for p in P]
+        gP = _zeros_like_many(P)
         g_cls, g_reg = gP[:2 * stacked], gP[2 * stacked:4 * stacked]
         gwc, gbc, gwr, gbr = gP[4 * stacked:4 * stacked + 4]
         _, wcd = pack_conv(wc)
