@@ -226,7 +226,8 @@ def bnact_bwd(dy, z, scale, shift, mean, rstd, act, row_scale=None, gate=None, d
     C = z.shape[-1]
     HW = z.numel() // (B * C)
     dz = torch.empty_like(z)
-    dgamma, dbeta = _zeros((C,), z), _zeros((C,), z)
+    gb = _zeros((2 * C,), z)
+    dgamma, dbeta = gb[:C], gb[C:]
     a = N.BnActBwdArgs(N.f32(dy, 'dy'), N.f32(z, 'z'), N.f32(dz), N.f32(scale), N.f32(shift), N.f32(mean, 'mean'),
                        N.f32(rstd), N.f32(dgamma), N.f32(dbeta), N.f32(row_scale), N.f32(gate), N.f32(dmean),
                        1.0 / HW, B, HW, C, act)
