@@ -240,12 +240,12 @@ extern "C" int effdet_relu_bwd(const float* dy, const float* y, float* dz, int64
 static void row_grid(int HW, int cvecs, int B, dim3* grid, int* rpb_out) {
     const int rows = rowpack_rows(cvecs);
     const int chunks = rowpack_chunks(cvecs);
-    // many more CTAs than resident slots (>= ~8 waves over 148 SMs x 2 CTAs) so the tail wave is cheap, but
-    // keep at least 4 row-iterations (one unrolled trip) per CTA
-    long long want_blocks = (148 * 16 + (long long)B * chunks - 1) / ((long long)B * chunks);
+    // ~4 waves of CTAs, at least 8 row-iterations each (measured: more, smaller CTAs are slower -- the per-CTA
+    // shared-memory reduction + atomics dominate)
+    long long want_blocks = (148 * 4 + (long long)B * chunks - 1) / ((long long)B * chunks);
     if (want_blocks < 1) want_blocks = 1;
     long long rpb = (HW + want_blocks - 1) / want_blocks;
-    if (rpb < (long long)rows * 4) rpb = (long long)rows * 4;
+    if (rpb < (long long)rows * 8) rpb = (long long)rows * 8;
     *rpb_out = (int)rpb;
     *grid = dim3(cdiv(HW, rpb), chunks, B);
 }
