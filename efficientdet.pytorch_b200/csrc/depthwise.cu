@@ -17,7 +17,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int K, int S>
+// BWD = true turns the same strip kernel into the stride-1 data gradient: taps are read 180-degree rotated, the
+// epilogue is a plain store (the caller passes dz as x and the mirrored pads)
+template <int K, int S, bool BWD>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                                      float* __restrict__ z, float* __restrict__ y, int B, int H, int W,
@@ -46,7 +48,8 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
         if (iy < 0 || iy >= H) continue;
         float4 wrow[K];
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) wrow[kx] = ldg4(wc + (ky * K + kx) * C);
+        for (int kx = 0; kx < K; ++kx)
+            wrow[kx] = BWD ? ldg4(wc + ((K - 1 - ky) * K + (K - 1 - kx)) * C) : ldg4(wc + (ky * K + kx) * C);
         const float* xr = xb + (long long)iy * W * C;
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) {
@@ -60,15 +63,20 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ x
             }
         }
     }
-    const float4 sc = ldg4(scale + cv * 4), sh = ldg4(shift + cv * 4);
+    float4 sc = f4zero(), sh = f4zero();
+    if (!BWD) { sc = ldg4(scale + cv * 4); sh = ldg4(shift + cv * 4); }
 #pragma unroll
     for (int i = 0; i < kTW; ++i) {
         const int ox = ox0 + i;
         if (ox >= Wo) break;
         const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cv * 4;
-        st4(z + o, acc[i]);
-        const float4 u = f4fma(acc[i], sc, sh);
-        st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
+        if (BWD) {
+            st4(y + o, acc[i]);
+        } else {
+            st4(z + o, acc[i]);
+            const float4 u = f4fma(acc[i], sc, sh);
+            st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
+        }
     }
 }
 
@@ -275,7 +283,10 @@ extern "C" int effdet_dwconv_fwd(const float* x, const float* w_kkc, const float
     EFFDET_DEVICE(device);
     const long long total = (long long)B * Ho * cdiv(Wo, kTW) * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
-    DW_DISPATCH(dw_fwd_kernel, <<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo))
+    if (k == 3 && stride == 1) dw_fwd_kernel<3, 1, false><<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo);
+    else if (k == 3) dw_fwd_kernel<3, 2, false><<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo);
+    else if (stride == 1) dw_fwd_kernel<5, 1, false><<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo);
+    else dw_fwd_kernel<5, 2, false><<<cdiv(total, 256), 256, 0, st>>>(x, w_kkc, scale, shift, z, y, B, H, W, C, pad_t, pad_l, Ho, Wo);
     return launch_status("dw_fwd_kernel");
 }
 
@@ -287,8 +298,16 @@ extern "C" int effdet_dwconv_bwd_data(const float* dz, const float* w_kkc, float
     int s = dw_check("dwconv_bwd_data", B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo);
     if (s) return s;
     EFFDET_DEVICE(device);
-    const long long total = (long long)B * H * W * (C / 4);
     cudaStream_t st = (cudaStream_t)stream;
+    if (stride == 1 && Ho == H && Wo == W) {
+        // stride 1: the data gradient is the same strip convolution with rotated taps and mirrored pads
+        const long long strips = (long long)B * H * cdiv(W, kTW) * (C / 4);
+        const int pt = k - 1 - pad_t, pl = k - 1 - pad_l;
+        if (k == 3) dw_fwd_kernel<3, 1, true><<<cdiv(strips, 256), 256, 0, st>>>(dz, w_kkc, nullptr, nullptr, nullptr, dx, B, H, W, C, pt, pl, H, W);
+        else dw_fwd_kernel<5, 1, true><<<cdiv(strips, 256), 256, 0, st>>>(dz, w_kkc, nullptr, nullptr, nullptr, dx, B, H, W, C, pt, pl, H, W);
+        return launch_status("dw_fwd_kernel<bwd>");
+    }
+    const long long total = (long long)B * H * W * (C / 4);
     DW_DISPATCH(dw_bwd_data_kernel, <<<cdiv(total, 256), 256, 0, st>>>(dz, w_kkc, dx, B, H, W, C, pad_t, pad_l, Ho, Wo))
     return launch_status("dw_bwd_data_kernel");
 }
