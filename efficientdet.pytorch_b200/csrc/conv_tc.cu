@@ -180,8 +180,8 @@ struct FwdSmem {
 
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
 template <int BN, int STAGES, bool MB>
-__global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
-conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args p, const int M, const int HW, const int kblocks) {
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effdet_conv_args& p, const int M, const int HW,
+                                             const int kblocks, const int m0, const int n0) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,7 +192,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
     float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [3][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BN;
     const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
     const int KT = taps * kblocks;
     for (int i = threadIdx.x; i < BN; i += kFwdThreads) {
@@ -399,6 +398,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const effdet_conv_args 
         tc_fence_after();
         tmem_dealloc<BN>(tmem_base);
     }
+}
+
+template <int BN, int STAGES, bool MB>
+__global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
+conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ effdet_conv_args p, const int M, const int HW,
+               const int kblocks) {
+    conv_tc_body<BN, STAGES, MB>(wmap, p, M, HW, kblocks, blockIdx.x * kTileM, blockIdx.y * BN);
+}
+
+// Several pyramid levels that share one weight tensor (RetinaHead runs the same convs on P3..P7,
+// models/retinahead.py:131-132) in ONE launch: the M tiles of all levels are concatenated so the small
+// levels (a handful of CTAs each) ride along with the large ones instead of paying their own latency-bound launch.
+constexpr int kMaxLevels = 8;
+struct ConvMultiArgs {
+    effdet_conv_args lv[kMaxLevels];
+    int tile_begin[kMaxLevels + 1];
+    int nlevels;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+conv_tc_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks) {
+    const int tile = blockIdx.x;
+    int l = 0;
+    while (l + 1 < ma.nlevels && tile >= ma.tile_begin[l + 1]) ++l;
+    const effdet_conv_args& p = ma.lv[l];
+    conv_tc_body<BN, STAGES, false>(wmap, p, p.B * p.H * p.W, p.H * p.W, kblocks, (tile - ma.tile_begin[l]) * kTileM,
+                                    blockIdx.y * BN);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -821,6 +848,48 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g);
 
+int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return fail(EFFDET_ERR_UNSUPPORTED, "conv2d_multi(tc): cuTensorMapEncodeTiled unavailable");
+    const effdet_conv_args* a = &levels[0];
+    const int taps = a->ksize * a->ksize;
+    const int kpad = conv_tc_kpad(a->Cin);
+    const int kblocks = kpad / kTileK;
+    const int BN = a->Cout <= 64 ? 64 : (a->Cout <= 128 ? 128 : 256);
+    CUtensorMap map;
+    const cuuint64_t gdim[3] = {(cuuint64_t)taps * kpad, (cuuint64_t)a->Cout, 2};
+    const cuuint64_t gstr[2] = {(cuuint64_t)taps * kpad * 2, (cuuint64_t)a->Cout * taps * kpad * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)BN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_tc), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    ConvMultiArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.nlevels = nlevels;
+    int tiles = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        ma.lv[l] = levels[l];
+        ma.tile_begin[l] = tiles;
+        tiles += cdiv((long long)levels[l].B * levels[l].H * levels[l].W, kTileM);
+    }
+    for (int l = nlevels; l <= kMaxLevels; ++l) ma.tile_begin[l] = tiles;
+    dim3 grid(tiles, cdiv(a->Cout, BN));
+#define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
+    do {                                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_multi_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             FwdSmem<BN_, ST_>::kBytes);                                                  \
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): smem opt-in: %s", cudaGetErrorString(e)); \
+        conv_tc_multi_kernel<BN_, ST_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks);           \
+    } while (0)
+    if (BN == 64) EFFDET_TCM_LAUNCH(64, 4);
+    else if (BN == 128) EFFDET_TCM_LAUNCH(128, 3);
+    else EFFDET_TCM_LAUNCH(256, 2);
+#undef EFFDET_TCM_LAUNCH
+    return launch_status("conv_tc_multi_kernel");
+}
+
 bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
     if (a->precision != 1 || a->Cin % 4 || a->Cout % 4 || a->Cin < 16 || a->Cout < 16) return false;
     WgGeom g;
@@ -939,6 +1008,33 @@ int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
 using namespace effdet;
 
 extern "C" int effdet_conv_tc_kpad(int channels) { return conv_tc_kpad(channels); }
+
+extern "C" int effdet_conv2d_multi(const effdet_conv_args* levels, int nlevels, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(levels && nlevels >= 1 && nlevels <= kMaxLevels, "conv2d_multi: 1..%d levels", kMaxLevels);
+    bool tc = true;
+    for (int l = 0; l < nlevels; ++l) {
+        const effdet_conv_args* a = &levels[l];
+        EFFDET_REQUIRE(a->x && a->w && a->y, "conv2d_multi: null tensor");
+        EFFDET_REQUIRE(a->Cin == levels[0].Cin && a->Cout == levels[0].Cout && a->ksize == levels[0].ksize &&
+                           a->act == levels[0].act && a->w == levels[0].w && a->w_tc == levels[0].w_tc &&
+                           a->bias == levels[0].bias,
+                       "conv2d_multi: all levels must share weights, bias, channels and activation");
+        const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
+        tc = tc && conv_tc_eligible(a) && !mb && (long long)a->B * a->H * a->W < (1ll << 31);
+        EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->residual) && aligned16(a->mask_src) &&
+                           a->x_bstride % 4 == 0 && a->y_bstride % 4 == 0 && a->r_bstride % 4 == 0 && a->m_bstride % 4 == 0,
+                       "conv2d_multi: alignment");
+    }
+    if (tc && nlevels > 1) {
+        EFFDET_DEVICE(device);
+        return conv_tc_multi_launch(levels, nlevels, (cudaStream_t)stream);
+    }
+    for (int l = 0; l < nlevels; ++l) {          // exact-fp32 mode / unsupported shapes: one launch per level
+        int s = effdet_conv2d(&levels[l], device, stream);
+        if (s) return s;
+    }
+    return EFFDET_OK;
+}
 
 extern "C" int effdet_pack_conv_weight_tc(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,
                                           int device, effdet_stream_t stream) {

@@ -87,6 +87,7 @@ _TAIL = [_INT, _P]  # (device, stream)
 # name -> argument types (everything returns int unless noted); mirrors include/effdet_b200.h
 SIGNATURES = {
     'effdet_conv2d': [ctypes.POINTER(ConvArgs)] + _TAIL,
+    'effdet_conv2d_multi': [ctypes.POINTER(ConvArgs), _INT] + _TAIL,
     'effdet_conv2d_wgrad': [ctypes.POINTER(WgradArgs)] + _TAIL,
     'effdet_pack_conv_weight': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_pack_conv_weight_tc': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
@@ -229,7 +230,7 @@ class Profiler:
     def conv_flops(self, pred):
         fl, ms_tot, n = 0.0, 0.0, 0
         for name, t, ms in self._ms():
-            if name == 'effdet_conv2d' and t is not None and pred(t):
+            if name in ('effdet_conv2d', 'effdet_conv2d_multi') and t is not None and pred(t):
                 fl += 2.0 * t[0] * t[1] * t[2] * t[5] * t[5] * t[3] * t[4]
                 ms_tot += ms
                 n += 1
@@ -255,6 +256,10 @@ def call(name, dev_tensor, *args, nbytes=0, flops=0):
         if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
             a = args[0]
             tag = (a.B, a.H, a.W, a.Cin, a.Cout, a.ksize)
+        elif name == 'effdet_conv2d_multi':
+            arr, nl = args[0], args[1]
+            pix = sum(arr[i].B * arr[i].H * arr[i].W for i in range(nl))
+            tag = (1, pix, 1, arr[0].Cin, arr[0].Cout, arr[0].ksize)      # B*H*W folded into one factor
         if tag is not None and not flops:
             flops = 2.0 * tag[0] * tag[1] * tag[2] * tag[5] * tag[5] * tag[3] * tag[4]
             if not nbytes:

@@ -201,6 +201,37 @@ def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_
     return (y, z) if save_z else y
 
 
+def conv2d_multi_raw(dev_t, levels, wf, Cin, Cout, k, bias=None, act=ACT_NONE, w_tc=None):
+    """One launch over several feature maps that share weights.  levels: dicts with x_ptr, x_bs, y_ptr, y_bs,
+    B, H, W and optional res_ptr/res_bs, mask_ptr/mask_bs."""
+    nl = len(levels)
+    arr = (N.ConvArgs * nl)()
+    wfp, bp = N.f32(wf, 'packed weight'), N.f32(bias, 'bias')
+    tcp = w_tc.data_ptr() if w_tc is not None else None
+    for i, lv in enumerate(levels):
+        arr[i] = N.ConvArgs(lv['x_ptr'], lv['x_bs'], wfp, lv['y_ptr'], lv['y_bs'], None, bp, None, None, None, None,
+                            lv.get('res_ptr'), lv.get('res_bs', 0), lv.get('mask_ptr'), lv.get('mask_bs', 0),
+                            lv['B'], lv['H'], lv['W'], Cin, Cout, k, act, tcp)
+    N.call('effdet_conv2d_multi', dev_t, arr, nl)
+
+
+def conv2d_multi(xs, wf, Cout, k, bias=None, act=ACT_NONE, w_tc=None, residuals=None, masks=None):
+    """xs: list of NHWC tensors (same channel count) -> list of NHWC outputs, one kernel launch."""
+    ys, levels = [], []
+    for i, x in enumerate(xs):
+        B, H, W, Cin = x.shape
+        y = _empty((B, H, W, Cout), x)
+        ys.append(y)
+        lv = dict(x_ptr=N.f32(x, 'x'), x_bs=H * W * Cin, y_ptr=N.f32(y), y_bs=H * W * Cout, B=B, H=H, W=W)
+        if residuals is not None and residuals[i] is not None:
+            lv.update(res_ptr=N.f32(residuals[i], 'residual'), res_bs=H * W * Cout)
+        if masks is not None and masks[i] is not None:
+            lv.update(mask_ptr=N.f32(masks[i], 'mask_src'), mask_bs=H * W * Cout)
+        levels.append(lv)
+    conv2d_multi_raw(xs[0], levels, wf, xs[0].shape[3], Cout, k, bias=bias, act=act, w_tc=w_tc)
+    return ys
+
+
 def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False):
     ws_x = ws_dy = None
     if tc:
@@ -565,7 +596,8 @@ class BiFPNLayerFn(torch.autograd.Function):
 class RetinaHeadFn(torch.autograd.Function):
     """args: nlevels, num_anchors, num_classes, stacked, feats..., then parameters in the order
     cls_convs (w,b)*stacked, reg_convs (w,b)*stacked, retina_cls w,b, retina_reg w,b.
-    Returns (cls [B, sum(HWA), K] after sigmoid, reg [B, sum(HWA), 4]) -- already concatenated."""
+    Returns (cls [B, sum(HWA), K] after sigmoid, reg [B, sum(HWA), 4]) -- already concatenated.
+    Every layer runs on all pyramid levels in one launch (the weights are shared between levels)."""
 
     @staticmethod
     def forward(ctx, nl, A, K, stacked, *args):
@@ -581,38 +613,37 @@ class RetinaHeadFn(torch.autograd.Function):
             tot += f.shape[1] * f.shape[2] * A
         cls_all = _empty((B, tot, K), feats[0])
         reg_all = _empty((B, tot, 4), feats[0])
-        acts = []
-        wcf, _ = pack_conv(wc)
-        wrf, _ = pack_conv(wr)
-        for lv, f in enumerate(feats):
-            _, H, W, Cin = f.shape
-            c, r = f, f
-            ca, ra = [f], [f]
+        towers = []
+        for tp in (cls_p, reg_p):
+            acts = [feats]
+            cur = feats
             for i in range(stacked):
-                wf, _ = pack_conv(cls_p[2 * i])
-                c = conv2d(c, wf, F, 3, bias=cls_p[2 * i + 1].detach(), act=ACT_RELU, w_tc=tc_packs(cls_p[2 * i])[0])
-                ca.append(c)
-            for i in range(stacked):
-                wf, _ = pack_conv(reg_p[2 * i])
-                r = conv2d(r, wf, F, 3, bias=reg_p[2 * i + 1].detach(), act=ACT_RELU, w_tc=tc_packs(reg_p[2 * i])[0])
-                ra.append(r)
-            conv2d_raw(f, N.f32(c), H * W * F, wcf, cls_all.data_ptr() + 4 * offs[lv] * K, tot * K, B, H, W, F,
-                       A * K, 3, bias=bc.detach(), act=ACT_SIGMOID, w_tc=tc_packs(wc)[0])
-            conv2d_raw(f, N.f32(r), H * W * F, wrf, reg_all.data_ptr() + 4 * offs[lv] * 4, tot * 4, B, H, W, F,
-                       A * 4, 3, bias=br.detach(), w_tc=tc_packs(wr)[0])
-            acts.append((ca, ra))
+                wf, _ = pack_conv(tp[2 * i])
+                cur = conv2d_multi(cur, wf, F, 3, bias=tp[2 * i + 1].detach(), act=ACT_RELU, w_tc=tc_packs(tp[2 * i])[0])
+                acts.append(cur)
+            towers.append(acts)          # acts[i][lv]: input of conv i (acts[stacked] = tower output)
+        for (acts, w, bias, out, width, act) in ((towers[0], wc, bc, cls_all, K, ACT_SIGMOID),
+                                                 (towers[1], wr, br, reg_all, 4, ACT_NONE)):
+            wf, _ = pack_conv(w)
+            levels = []
+            for lv, t in enumerate(acts[stacked]):
+                _, H, W, _ = t.shape
+                levels.append(dict(x_ptr=N.f32(t), x_bs=H * W * F, y_ptr=out.data_ptr() + 4 * offs[lv] * width,
+                                   y_bs=tot * width, B=B, H=H, W=W))
+            conv2d_multi_raw(feats[0], levels, wf, F, A * width, 3, bias=bias.detach(), act=act, w_tc=tc_packs(w)[0])
         ctx.meta = (nl, A, K, stacked, offs, tot)
-        ctx.keep = (feats, P, acts, cls_all)
+        ctx.keep = (feats, P, towers, cls_all)
         return cls_all, reg_all
 
     @staticmethod
     def backward(ctx, dcls, dreg):
         nl, A, K, stacked, offs, tot = ctx.meta
-        feats, P, acts, cls_all = ctx.keep
+        feats, P, towers, cls_all = ctx.keep
         cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
         wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
         B = feats[0].shape[0]
         F = cls_p[0].shape[0]
+        Cin = feats[0].shape[3]
         dcls, dreg = _contig(dcls), _contig(dreg)
         dzc = torch.empty_like(dcls)
         N.call('effdet_sigmoid_bwd', dcls, N.f32(dcls), N.f32(cls_all), N.f32(dzc), dcls.numel(),
@@ -620,37 +651,37 @@ class RetinaHeadFn(torch.autograd.Function):
         gP = _zeros_like_many(P)
         g_cls, g_reg = gP[:2 * stacked], gP[2 * stacked:4 * stacked]
         gwc, gbc, gwr, gbr = gP[4 * stacked:4 * stacked + 4]
-        _, wcd = pack_conv(wc)
-        _, wrd = pack_conv(wr)
-        dfeats = []
-        for lv, f in enumerate(feats):
-            _, H, W, Cin = f.shape
-            ca, ra = acts[lv]
-            outs = []
-            tc = tc_enabled()
-            for (tower, tp, tg, wl, gwl, gbl, wld, dptr, width) in (
-                    (ca, cls_p, g_cls, wc, gwc, gbc, wcd, dzc.data_ptr() + 4 * offs[lv] * K, K),
-                    (ra, reg_p, g_reg, wr, gwr, gbr, wrd, dreg.data_ptr() + 4 * offs[lv] * 4, 4)):
-                top = tower[stacked]
-                Co = A * width
-                conv_wgrad_raw(f, N.f32(top), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3, tc=tc)
-                d = _empty((B, H, W, F), f)
-                bs = H * W * F
-                conv2d_raw(f, dptr, tot * width, wld, N.f32(d), bs, B, H, W, Co, F, 3, mask_ptr=N.f32(top), mask_bs=bs,
-                           w_tc=tc_packs(wl)[1])
-                for i in range(stacked - 1, -1, -1):
-                    xin = tower[i]
-                    conv_wgrad(xin, d, tg[2 * i], tg[2 * i + 1], 3, tc=tc)
-                    _, wd = pack_conv(tp[2 * i])
-                    wdt = tc_packs(tp[2 * i])[1]
-                    if i > 0:
-                        d = conv2d(d, wd, F, 3, mask_src=xin, w_tc=wdt)
-                    else:
-                        d = conv2d(d, wd, Cin, 3, residual=outs[0] if outs else None, w_tc=wdt)
-                outs.append(d)
-            dfeats.append(outs[-1])
+        tc = tc_enabled()
+        dfeat = None
+        for (acts, tp, tg, wl, gwl, gbl, dsrc, width) in ((towers[0], cls_p, g_cls, wc, gwc, gbc, dzc, K),
+                                                          (towers[1], reg_p, g_reg, wr, gwr, gbr, dreg, 4)):
+            Co = A * width
+            top = acts[stacked]
+            levels = []
+            d = []
+            for lv, t in enumerate(top):
+                _, H, W, _ = t.shape
+                dptr = dsrc.data_ptr() + 4 * offs[lv] * width
+                conv_wgrad_raw(t, N.f32(t), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3, tc=tc)
+                dl = _empty((B, H, W, F), t)
+                d.append(dl)
+                levels.append(dict(x_ptr=dptr, x_bs=tot * width, y_ptr=N.f32(dl), y_bs=H * W * F, B=B, H=H, W=W,
+                                   mask_ptr=N.f32(t), mask_bs=H * W * F))
+            _, wld = pack_conv(wl)
+            conv2d_multi_raw(feats[0], levels, wld, Co, F, 3, w_tc=tc_packs(wl)[1])
+            for i in range(stacked - 1, -1, -1):
+                xin = acts[i]
+                for lv in range(nl):
+                    conv_wgrad(xin[lv], d[lv], tg[2 * i], tg[2 * i + 1], 3, tc=tc)
+                _, wd = pack_conv(tp[2 * i])
+                wdt = tc_packs(tp[2 * i])[1]
+                if i > 0:
+                    d = conv2d_multi(d, wd, F, 3, w_tc=wdt, masks=xin)
+                else:
+                    d = conv2d_multi(d, wd, Cin, 3, w_tc=wdt, residuals=dfeat)
+            dfeat = d
         ctx.keep = None
-        return (None, None, None, None) + tuple(dfeats) + tuple(gP)
+        return (None, None, None, None) + tuple(dfeat) + tuple(gP)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -73,6 +73,10 @@ typedef struct {
                               tensor cores as a bf16x3 split-precision implicit GEMM (~2^-16 per product) */
 } effdet_conv_args;
 int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream);
+/* The same convolution (shared w / w_tc / bias / act, channels, ksize) applied to `nlevels` (<= 8) feature maps of
+ * different sizes in ONE launch -- RetinaHead.forward runs every layer on P3..P7 with the same weights
+ * (models/retinahead.py:131-132).  Falls back to one launch per level in exact-fp32 mode. */
+int effdet_conv2d_multi(const effdet_conv_args* levels, int nlevels, int device, effdet_stream_t stream);
 
 /* Weight gradient (and optional bias gradient) of the convolution above.
  *   dw[n,c,ky,kx] += sum_{b,p} x[b,p+tap,c]*a_scale[b,c] * dy[b,p,n]     (OIHW, as .grad)
