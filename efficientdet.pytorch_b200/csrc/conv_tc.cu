@@ -729,6 +729,145 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
     }
 }
 
+// Multi-level variant: the pixel chunks of several pyramid levels (same weights, e.g. the five RetinaHead levels)
+// form one long GEMM-K dimension, so one launch covers them all; each chunk looks up its level's tensor maps and
+// pixel-box geometry.
+constexpr int kWgMaxLevels = 8;
+struct WgMaps {
+    CUtensorMap dy[kWgMaxLevels];
+    CUtensorMap x[kWgMaxLevels];
+};
+struct WgMultiArgs {
+    WgGeom g[kWgMaxLevels];
+    int chunk_begin[kWgMaxLevels + 1];
+    int nlevels;
+    float* dw;
+    int Cin, Cout, ksize;
+};
+
+template <int BC, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+wgrad_tc2_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgMultiArgs a, const int chunks_per_split,
+                       const int ctiles) {
+    using S = WgSmem<BC, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ct = blockIdx.x % ctiles, nt = blockIdx.x / ctiles;
+    const int c0 = ct * BC, n0 = nt * kTileM;
+    const int tap = blockIdx.y;
+    const int pad = a.ksize / 2;
+    const int dy = tap / a.ksize - pad, dx = tap % a.ksize - pad;
+    const int nchunks = a.chunk_begin[a.nlevels];
+    const int ch_begin = blockIdx.z * chunks_per_split;
+    const int ch_end = min(nchunks, ch_begin + chunks_per_split);
+    const int KT = ch_end - ch_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<BC>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr int GROUP = kTileK * 128;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int l = 0;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                const int chg = ch_begin + kt;
+                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
+                const WgGeom& g = a.g[l];
+                int ch = chg - a.chunk_begin[l];
+                const int bx = ch % g.nbx;
+                ch /= g.nbx;
+                const int by = ch % g.nby;
+                const int bb = ch / g.nby;
+                const int x0 = bx * g.Wb, y0 = by * g.Hb, b0 = bb * g.Bb;
+                const uint32_t bytes = (uint32_t)(2 * (kTileM / 64 + BC / 64) * g.kstage * 128);
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], bytes);
+                uint8_t* a_hi = smem + s * S::kStage;
+                uint8_t* b_hi = a_hi + 2 * S::kA;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                    for (int q = 0; q < kTileM / 64; ++q)
+                        tma_load_5d(a_hi + pl * S::kA + q * GROUP, &maps.dy[l], &full_bar[s], n0 + q * 64, x0, y0, b0, pl);
+#pragma unroll
+                    for (int q = 0; q < BC / 64; ++q)
+                        tma_load_5d(b_hi + pl * S::kB + q * GROUP, &maps.x[l], &full_bar[s], c0 + q * 64, x0 + dx, y0 + dy, b0, pl);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTileM, BC, 1, 1);
+            constexpr uint32_t LBO = GROUP, SBO = 1024;
+            int l = 0;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                const int chg = ch_begin + kt;
+                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
+                const int ksteps = a.g[l].kstage / 16;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t ko = k * 2 * SBO;
+                    const uint64_t dah = umma_desc(a_hi + ko, LBO, SBO), dal = umma_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = umma_desc(b_hi + ko, LBO, SBO), dbl = umma_desc(b_lo + ko, LBO, SBO);
+                    umma_bf16(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int n = n0 + warp * 32 + lane;
+        const int kk = a.ksize * a.ksize;
+#pragma unroll 1
+        for (int cc = 0; cc < BC / 32; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+            if (n >= a.Cout) continue;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int c = c0 + cc * 32 + q;
+                if (c < a.Cin) atomicAdd(a.dw + ((long long)n * a.Cin + c) * kk + tap, __uint_as_float(acc[q]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<BC>(tmem_base);
+    }
+}
+
 // fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ a_scale,
                                                            __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad) {
@@ -971,6 +1110,66 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     return launch_status("wgrad_tc2_kernel");
 }
 
+// all levels in one launch; returns 1 when some level cannot use the TMA path (caller falls back per level)
+int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStream_t st) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc || nlevels > kWgMaxLevels) return 1;
+    WgMaps maps;
+    WgMultiArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    const effdet_wgrad_args* a0 = &levels[0];
+    const int cin_pad = conv_tc_kpad(a0->Cin), cout_pad = conv_tc_kpad(a0->Cout);
+    int chunks = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        const effdet_wgrad_args* a = &levels[l];
+        if (!a->ws_x || !a->ws_dy || a->a_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
+        ma.chunk_begin[l] = chunks;
+        chunks += ma.g[l].nbx * ma.g[l].nby * ma.g[l].nbb;
+    }
+    for (int l = nlevels; l <= kWgMaxLevels; ++l) ma.chunk_begin[l] = chunks;
+    ma.nlevels = nlevels;
+    ma.dw = a0->dw;
+    ma.Cin = a0->Cin; ma.Cout = a0->Cout; ma.ksize = a0->ksize;
+    for (int l = 0; l < nlevels; ++l) {
+        const effdet_wgrad_args* a = &levels[l];
+        const int HW = a->H * a->W;
+        int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, nullptr, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
+        int s = launch_status("split_planes_kernel");
+        if (s) return s;
+        blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, nullptr, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
+        if ((s = launch_status("split_planes_kernel"))) return s;
+        if ((s = planes_map(enc, &maps.dy[l], a->ws_dy, a->B, a->H, a->W, cout_pad, ma.g[l]))) return s;
+        if ((s = planes_map(enc, &maps.x[l], a->ws_x, a->B, a->H, a->W, cin_pad, ma.g[l]))) return s;
+    }
+    for (int l = nlevels; l < kWgMaxLevels; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
+    const int taps = a0->ksize * a0->ksize;
+    const int BC = a0->Cin > 64 ? 256 : 64;
+    const int ctiles = cdiv(a0->Cin, BC), ntiles = cdiv(a0->Cout, kTileM);
+    int splits = (148 * 2) / (ctiles * ntiles * taps);
+    if (splits < 1) splits = 1;
+    if (splits > cdiv(chunks, 4)) splits = cdiv(chunks, 4);
+    int cps = cdiv(chunks, splits);
+    splits = cdiv(chunks, cps);
+    dim3 grid(ctiles * ntiles, taps, splits);
+    cudaError_t e;
+    if (BC == 256) {
+        constexpr int ST = 2;
+        e = cudaFuncSetAttribute(wgrad_tc2_multi_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<256, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad_multi(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc2_multi_kernel<256, ST><<<grid, kTcThreads, WgSmem<256, ST>::kBytes, st>>>(maps, ma, cps, ctiles);
+    } else {
+        constexpr int ST = 4;
+        e = cudaFuncSetAttribute(wgrad_tc2_multi_kernel<64, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<64, ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad_multi(tc): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc2_multi_kernel<64, ST><<<grid, kTcThreads, WgSmem<64, ST>::kBytes, st>>>(maps, ma, cps, ctiles);
+    }
+    return launch_status("wgrad_tc2_multi_kernel");
+}
+
 int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     {
         const int r = wgrad_tc2_launch(a, st);
@@ -1008,6 +1207,42 @@ int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
 using namespace effdet;
 
 extern "C" int effdet_conv_tc_kpad(int channels) { return conv_tc_kpad(channels); }
+
+namespace effdet {   // defined in conv_simt.cu
+int colsum_launch(const float* x, float* out, long long M, int N, long long HW, long long bstride, int device,
+                  effdet_stream_t stream);
+}
+
+extern "C" int effdet_conv2d_wgrad_multi(const effdet_wgrad_args* levels, int nlevels, int device, effdet_stream_t stream) {
+    EFFDET_REQUIRE(levels && nlevels >= 1, "conv2d_wgrad_multi: no levels");
+    bool same = true;
+    for (int l = 0; l < nlevels; ++l) {
+        const effdet_wgrad_args* a = &levels[l];
+        EFFDET_REQUIRE(a->x && a->dy && a->dw, "conv2d_wgrad_multi: null tensor");
+        same = same && a->dw == levels[0].dw && a->dbias == levels[0].dbias && a->Cin == levels[0].Cin &&
+               a->Cout == levels[0].Cout && a->ksize == levels[0].ksize && a->precision == 1 && wgrad_tc_eligible(a);
+    }
+    if (same && nlevels > 1) {
+        EFFDET_DEVICE(device);
+        const int r = wgrad_tc2_multi_launch(levels, nlevels, (cudaStream_t)stream);
+        if (r < 0) return r;
+        if (r == 0) {
+            if (levels[0].dbias)
+                for (int l = 0; l < nlevels; ++l) {
+                    const effdet_wgrad_args* a = &levels[l];
+                    const int s = colsum_launch(a->dy, a->dbias, (long long)a->B * a->H * a->W, a->Cout, (long long)a->H * a->W,
+                                                a->dy_bstride, device, stream);
+                    if (s) return s;
+                }
+            return EFFDET_OK;
+        }
+    }
+    for (int l = 0; l < nlevels; ++l) {
+        const int s = effdet_conv2d_wgrad(&levels[l], device, stream);
+        if (s) return s;
+    }
+    return EFFDET_OK;
+}
 
 extern "C" int effdet_conv2d_multi(const effdet_conv_args* levels, int nlevels, int device, effdet_stream_t stream) {
     EFFDET_REQUIRE(levels && nlevels >= 1 && nlevels <= kMaxLevels, "conv2d_multi: 1..%d levels", kMaxLevels);

@@ -89,6 +89,7 @@ SIGNATURES = {
     'effdet_conv2d': [ctypes.POINTER(ConvArgs)] + _TAIL,
     'effdet_conv2d_multi': [ctypes.POINTER(ConvArgs), _INT] + _TAIL,
     'effdet_conv2d_wgrad': [ctypes.POINTER(WgradArgs)] + _TAIL,
+    'effdet_conv2d_wgrad_multi': [ctypes.POINTER(WgradArgs), _INT] + _TAIL,
     'effdet_pack_conv_weight': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_pack_conv_weight_tc': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_colsum': [_P, _P, _I64, _INT] + _TAIL,
@@ -256,7 +257,7 @@ def call(name, dev_tensor, *args, nbytes=0, flops=0):
         if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
             a = args[0]
             tag = (a.B, a.H, a.W, a.Cin, a.Cout, a.ksize)
-        elif name == 'effdet_conv2d_multi':
+        elif name in ('effdet_conv2d_multi', 'effdet_conv2d_wgrad_multi'):
             arr, nl = args[0], args[1]
             pix = sum(arr[i].B * arr[i].H * arr[i].W for i in range(nl))
             tag = (1, pix, 1, arr[0].Cin, arr[0].Cout, arr[0].ksize)      # B*H*W folded into one factor

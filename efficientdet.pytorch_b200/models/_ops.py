@@ -244,6 +244,27 @@ def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, C
     N.call('effdet_conv2d_wgrad', dev_t, a)
 
 
+def conv_wgrad_multi(dev_t, levels, dw, dbias, Cin, Cout, k, tc=False):
+    """Weight gradient of one shared-weight layer over several feature maps, accumulated into dw/dbias by ONE
+    launch.  levels: dicts with x_ptr, x_bs, dy_ptr, dy_bs, B, H, W."""
+    nl = len(levels)
+    arr = (N.WgradArgs * nl)()
+    keep = []
+    lib = N.load()
+    kin, kout = lib.effdet_conv_tc_kpad(Cin), lib.effdet_conv_tc_kpad(Cout)
+    for i, lv in enumerate(levels):
+        ws_x = ws_dy = None
+        if tc:
+            npx = lv['B'] * lv['H'] * lv['W']
+            ws_x = torch.empty((2 * npx * kin,), device=dev_t.device, dtype=torch.bfloat16)
+            ws_dy = torch.empty((2 * npx * kout,), device=dev_t.device, dtype=torch.bfloat16)
+            keep += [ws_x, ws_dy]
+        arr[i] = N.WgradArgs(lv['x_ptr'], lv['x_bs'], lv['dy_ptr'], lv['dy_bs'], N.f32(dw, 'dw'), N.f32(dbias, 'dbias'),
+                             None, lv['B'], lv['H'], lv['W'], Cin, Cout, k, 1 if tc else 0,
+                             ws_x.data_ptr() if ws_x is not None else None, ws_dy.data_ptr() if ws_dy is not None else None)
+    N.call('effdet_conv2d_wgrad_multi', dev_t, arr, nl)
+
+
 def conv_wgrad(x, dy, dw, dbias, k, a_scale=None, tc=False):
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
@@ -659,20 +680,25 @@ class RetinaHeadFn(torch.autograd.Function):
             top = acts[stacked]
             levels = []
             d = []
+            wl_levels = []
             for lv, t in enumerate(top):
                 _, H, W, _ = t.shape
                 dptr = dsrc.data_ptr() + 4 * offs[lv] * width
-                conv_wgrad_raw(t, N.f32(t), H * W * F, dptr, tot * width, gwl, gbl, B, H, W, F, Co, 3, tc=tc)
+                wl_levels.append(dict(x_ptr=N.f32(t), x_bs=H * W * F, dy_ptr=dptr, dy_bs=tot * width, B=B, H=H, W=W))
                 dl = _empty((B, H, W, F), t)
                 d.append(dl)
                 levels.append(dict(x_ptr=dptr, x_bs=tot * width, y_ptr=N.f32(dl), y_bs=H * W * F, B=B, H=H, W=W,
                                    mask_ptr=N.f32(t), mask_bs=H * W * F))
+            conv_wgrad_multi(feats[0], wl_levels, gwl, gbl, F, Co, 3, tc=tc)
             _, wld = pack_conv(wl)
             conv2d_multi_raw(feats[0], levels, wld, Co, F, 3, w_tc=tc_packs(wl)[1])
             for i in range(stacked - 1, -1, -1):
                 xin = acts[i]
-                for lv in range(nl):
-                    conv_wgrad(xin[lv], d[lv], tg[2 * i], tg[2 * i + 1], 3, tc=tc)
+                ci = xin[0].shape[3]
+                conv_wgrad_multi(feats[0], [dict(x_ptr=N.f32(xin[lv]), x_bs=xin[lv].shape[1] * xin[lv].shape[2] * ci,
+                                                 dy_ptr=N.f32(d[lv]), dy_bs=d[lv].shape[1] * d[lv].shape[2] * F,
+                                                 B=B, H=xin[lv].shape[1], W=xin[lv].shape[2]) for lv in range(nl)],
+                                 tg[2 * i], tg[2 * i + 1], ci, F, 3, tc=tc)
                 _, wd = pack_conv(tp[2 * i])
                 wdt = tc_packs(tp[2 * i])[1]
                 if i > 0:

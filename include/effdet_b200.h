@@ -95,6 +95,9 @@ typedef struct {
                               NULL -> the gather-producer tensor-core kernel is used instead */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
+/* Weight gradient of one shared-weight layer accumulated over `nlevels` feature maps in one launch (all levels
+ * must name the same dw / dbias); falls back to one launch per level when a level cannot use the TMA path. */
+int effdet_conv2d_wgrad_multi(const effdet_wgrad_args* levels, int nlevels, int device, effdet_stream_t stream);
 
 /* OIHW -> [k*k][Cin][Cout] (forward) and, if w_dgrad != NULL, the 180-degree-rotated transpose
  * [k*k][Cout][Cin] that turns the data gradient into the same implicit GEMM. */
