@@ -14,7 +14,7 @@ namespace effdet {
 bool conv_tc_eligible(const effdet_conv_args* a);
 int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st);
 bool wgrad_tc_eligible(const effdet_wgrad_args* a);
-int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st);
+int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st, bool* dbias_done);
 
 constexpr int kBM = 128;   // output pixels per CTA
 constexpr int kBK = 16;    // reduction slice (channels of one tap)
@@ -427,8 +427,9 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     const int taps = a->ksize * a->ksize;
     cudaStream_t st = (cudaStream_t)stream;
     int s = EFFDET_OK;
+    bool dbias_done = false;
     if (wgrad_tc_eligible(a)) {
-        s = wgrad_tc_launch(a, st);
+        s = wgrad_tc_launch(a, st, &dbias_done);
     } else {
     int BC, BN;
     if (a->Cin <= 32) { BC = 32; BN = 128; }
@@ -451,7 +452,7 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     s = launch_status("conv_wgrad_kernel");
     }
     if (s) return s;
-    if (a->dbias) return colsum_launch(a->dy, a->dbias, M, a->Cout, HW, a->dy_bstride, device, stream);
+    if (a->dbias && !dbias_done) return colsum_launch(a->dy, a->dbias, M, a->Cout, HW, a->dy_bstride, device, stream);
     return EFFDET_OK;
 }
 

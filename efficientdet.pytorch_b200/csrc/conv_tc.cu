@@ -897,6 +897,78 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
     }
 }
 
+// split + per-channel column sums in one pass: the weight gradient's dy operand is split into planes AND reduced
+// into the bias gradient (dbias[n] += sum over pixels) while it streams by, so no second read of dy.
+__global__ void __launch_bounds__(256) split_planes_colsum_kernel(const float* __restrict__ x, long long bstride,
+                                                                  __nv_bfloat16* __restrict__ out, float* __restrict__ colsum,
+                                                                  int B, int HW, int C, int Cpad, int rows_per_block) {
+    __shared__ float red[256 * 8];
+    const int cv8 = Cpad / 8;
+    const int cvb = cv8 < 256 ? cv8 : 256;
+    const int rows = 256 / cvb;
+    const int tr = threadIdx.x / cvb, tc = threadIdx.x - tr * cvb;
+    const int j = blockIdx.y * cvb + tc;
+    const bool active = tr < rows && j < cv8;
+    const long long nrows = (long long)B * HW;
+    const long long plane = nrows * Cpad;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    if (active) {
+        const int c = j * 8;
+        const long long r_begin = (long long)blockIdx.x * rows_per_block;
+        const long long r_end = min(nrows, r_begin + rows_per_block);
+        for (long long row = r_begin + tr; row < r_end; row += rows) {
+            const int b = (int)(row / HW);
+            const long long pix = row - (long long)b * HW;
+            float4 v0 = f4zero(), v1 = f4zero();
+            if (c < C) {
+                const float* q = x + (long long)b * bstride + pix * C + c;
+                v0 = ldg4(q);
+                if (c + 4 < C) v1 = ldg4(q + 4);
+            }
+            uint4 hi, lo;
+            split8(v0, v1, hi, lo);
+            *reinterpret_cast<uint4*>(out + row * Cpad + c) = hi;
+            *reinterpret_cast<uint4*>(out + plane + row * Cpad + c) = lo;
+            s[0] += v0.x; s[1] += v0.y; s[2] += v0.z; s[3] += v0.w;
+            s[4] += v1.x; s[5] += v1.y; s[6] += v1.z; s[7] += v1.w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+    __syncthreads();
+    if (tr == 0 && j < cv8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float acc = 0.f;
+            for (int r = 0; r < rows; ++r) acc += red[(r * cvb + tc) * 8 + i];
+            const int c = j * 8 + i;
+            if (c < C) atomicAdd(colsum + c, acc);
+        }
+    }
+}
+
+static int split_dy_launch(const effdet_wgrad_args* a, int cout_pad, cudaStream_t st) {
+    const int HW = a->H * a->W;
+    if (!a->dbias) {
+        int blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, nullptr, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
+        return launch_status("split_planes_kernel");
+    }
+    const int cv8 = cout_pad / 8;
+    const int cvb = cv8 < 256 ? cv8 : 256;
+    const int rows = 256 / cvb;
+    const long long nrows = (long long)a->B * HW;
+    long long rpb = (nrows + 148 * 4 - 1) / (148 * 4);
+    if (rpb < (long long)rows * 8) rpb = (long long)rows * 8;
+    dim3 grid(cdiv(nrows, rpb), cdiv(cv8, cvb));
+    split_planes_colsum_kernel<<<grid, 256, 0, st>>>(a->dy, a->dy_bstride, (__nv_bfloat16*)a->ws_dy, a->dbias, a->B, HW, a->Cout,
+                                                    cout_pad, (int)rpb);
+    return launch_status("split_planes_colsum_kernel");
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight pre-split: OIHW fp32 -> bf16 planes [2][rows][taps][Kpad] (K-major, zero padded)
 //   forward pack : rows = Cout, k = Cin,  W[n][c][tap]
@@ -1077,10 +1149,7 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
     int s = launch_status("split_planes_kernel");
     if (s) return s;
-    blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, nullptr, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
-    if ((s = launch_status("split_planes_kernel"))) return s;
+    if ((s = split_dy_launch(a, cout_pad, st))) return s;      // also accumulates the bias gradient
     CUtensorMap mdy, mx;
     if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;
     if ((s = planes_map(enc, &mx, a->ws_x, a->B, a->H, a->W, cin_pad, g))) return s;
@@ -1138,10 +1207,7 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
         split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, nullptr, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
         int s = launch_status("split_planes_kernel");
         if (s) return s;
-        blocks = cdiv((long long)a->B * HW * (cout_pad / 8), 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        split_planes_kernel<<<blocks, 256, 0, st>>>(a->dy, a->dy_bstride, nullptr, (__nv_bfloat16*)a->ws_dy, a->B, HW, a->Cout, cout_pad);
-        if ((s = launch_status("split_planes_kernel"))) return s;
+        if ((s = split_dy_launch(a, cout_pad, st))) return s;  // also accumulates the bias gradient
         if ((s = planes_map(enc, &maps.dy[l], a->ws_dy, a->B, a->H, a->W, cout_pad, ma.g[l]))) return s;
         if ((s = planes_map(enc, &maps.x[l], a->ws_x, a->B, a->H, a->W, cin_pad, ma.g[l]))) return s;
     }
@@ -1170,9 +1236,11 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     return launch_status("wgrad_tc2_multi_kernel");
 }
 
-int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st) {
+int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st, bool* dbias_done) {
+    *dbias_done = false;
     {
         const int r = wgrad_tc2_launch(a, st);
+        if (r == 0) *dbias_done = true;     // the TMA path folds the bias gradient into its dy split pass
         if (r <= 0) return r;       // launched (0) or failed (<0); 1 = geometry unsupported -> gather kernel
     }
     const long long Mll = (long long)a->B * a->H * a->W;
@@ -1226,16 +1294,7 @@ extern "C" int effdet_conv2d_wgrad_multi(const effdet_wgrad_args* levels, int nl
         EFFDET_DEVICE(device);
         const int r = wgrad_tc2_multi_launch(levels, nlevels, (cudaStream_t)stream);
         if (r < 0) return r;
-        if (r == 0) {
-            if (levels[0].dbias)
-                for (int l = 0; l < nlevels; ++l) {
-                    const effdet_wgrad_args* a = &levels[l];
-                    const int s = colsum_launch(a->dy, a->dbias, (long long)a->B * a->H * a->W, a->Cout, (long long)a->H * a->W,
-                                                a->dy_bstride, device, stream);
-                    if (s) return s;
-                }
-            return EFFDET_OK;
-        }
+        if (r == 0) return EFFDET_OK;          // bias gradient was fused into the dy split pass
     }
     for (int l = 0; l < nlevels; ++l) {
         const int s = effdet_conv2d_wgrad(&levels[l], device, stream);
