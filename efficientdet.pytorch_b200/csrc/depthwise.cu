@@ -321,8 +321,6 @@ extern "C" int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* 
     if (s) return s;
     EFFDET_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Ho >= 16 && Wo >= 16) {
-        // tiled kernel: TH x TW = 16x16 outputs (stride 1) or 8x16 (stride 2), 32 channels per CTA
 #define EFFDET_DW_TILED(K_, S_, TH_, TW_)                                                                                  \
         do {                                                                                                              \
             constexpr int IH = (TH_ - 1) * S_ + K_, IW = (TW_ - 1) * S_ + K_;                                             \
@@ -339,13 +337,23 @@ extern "C" int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* 
             dw_bwd_weight_tiled_kernel<K_, S_, TH_, TW_><<<dim3((unsigned)gx, chunks), 256, smem, st>>>(                  \
                 x, dz, dw_c1kk, B, H, W, C, pad_t, pad_l, Ho, Wo, tiles_x, tiles_y);                                      \
         } while (0)
+    if (Ho >= 16 && Wo >= 16) {
+        // tiled kernel: TH x TW = 16x16 outputs (stride 1) or 8x16 (stride 2), 32 channels per CTA
         if (k == 3 && stride == 1) EFFDET_DW_TILED(3, 1, 16, 16);
         else if (k == 3 && stride == 2) EFFDET_DW_TILED(3, 2, 8, 16);
         else if (k == 5 && stride == 1) EFFDET_DW_TILED(5, 1, 16, 16);
         else EFFDET_DW_TILED(5, 2, 8, 16);
-#undef EFFDET_DW_TILED
         return launch_status("dw_bwd_weight_tiled_kernel");
     }
+    if (Ho >= 4 && Wo >= 4) {
+        // late stages (8x8 / 4x4 maps, many channels): one 8x8 tile per image and 32-channel chunk
+        if (k == 3 && stride == 1) EFFDET_DW_TILED(3, 1, 8, 8);
+        else if (k == 3 && stride == 2) EFFDET_DW_TILED(3, 2, 8, 8);
+        else if (k == 5 && stride == 1) EFFDET_DW_TILED(5, 1, 8, 8);
+        else EFFDET_DW_TILED(5, 2, 8, 8);
+        return launch_status("dw_bwd_weight_tiled_kernel");
+    }
+#undef EFFDET_DW_TILED
     const int cvecs = C / 4;
     const long long npix = (long long)B * Ho * cdiv(Wo, kTW);   // strips of kTW outputs
     const int rows = rowpack_rows(cvecs);
