@@ -211,7 +211,8 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(images_d, ann_d)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                      # one nvidia-smi poller per job, on rank 0's GPU
+        sampler.start()
     _native.reset_launch_count()
     ms = timed(lambda: step(images_d, ann_d), args.steps)
     launches = _native.launch_count() // max(args.steps, 1)
@@ -257,7 +258,8 @@ def run_ours(args):
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     # per-kernel breakdown with CUDA events around every C-ABI launch (extra profiled steps, rank 0)
     roofline, breakdown, cpu_base, kroof = None, None, None, None
