@@ -1005,7 +1005,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 bool conv_tc_eligible(const effdet_conv_args* a) {
     if (a->w_tc == nullptr || a->Cin % 4 || a->Cout % 4 || a->Cout < 16) return false;
     // measured (profiles/r01_bench_full_breakdown.json): the narrowest 1x1 layers are faster on the CUDA cores
-    if (a->ksize == 1 && a->Cin <= 32 && a->Cout <= 16 && getenv("EFFDET_TC_NARROW") == nullptr) return false;
+    if (a->ksize == 1 && (a->Cin < 24 || (a->Cin <= 32 && a->Cout <= 16))) return false;
     return true;
 }
 
