@@ -49,22 +49,79 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
     st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
 }
 
-constexpr int kStemP = 64;     // pixels staged per iteration
-constexpr int kStemMaxI = 7;   // taps per thread upper bound (27 / (256 / C0)) for C0 <= 64
-
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
-                                                         float* __restrict__ dw, int B, int H, int W, int C0, int Ho,
-                                                         int Wo) {
-    extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                    // [kStemP][28]  (27 taps, padded)
-    float* ds = sm + kStemP * 28;      // [kStemP][C0]
-    const int t = threadIdx.x;
-    const int IG = 256 / C0;           // tap groups
-    const int co = t % C0, ig = t / C0;
-    const bool worker = ig < IG;
-    float acc[kStemMaxI];
+// One thread per output pixel, all C0 = 4*NV channels in registers: the 27 input taps are fetched once per pixel
+// (not once per 4-channel group) and the weights are warp-broadcast 128-bit shared loads.
+template <int NV>
+__global__ void __launch_bounds__(128) stem_fwd_px_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          float* __restrict__ z, float* __restrict__ y, int B, int H, int W,
+                                                          int Ho, int Wo) {
+    constexpr int C0 = NV * 4;
+    __shared__ __align__(16) float ws[27 * C0];
+    __shared__ __align__(16) float sc_s[C0];
+    __shared__ __align__(16) float sh_s[C0];
+    for (int i = threadIdx.x; i < 27 * C0; i += blockDim.x) {
+        const int co = i % C0, tap = i / C0;
+        ws[i] = __ldg(w + co * 27 + tap);
+    }
+    for (int i = threadIdx.x; i < C0; i += blockDim.x) { sc_s[i] = __ldg(scale + i); sh_s[i] = __ldg(shift + i); }
+    __syncthreads();
+    const long long npix = (long long)B * Ho * Wo;
+    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int ox = (int)(pix % Wo);
+    const long long r = pix / Wo;
+    const int oy = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float v[27];
+    const float* xb = x + (long long)b * 3 * H * W;
 #pragma unroll
-    for (int j = 0; j < kStemMaxI; ++j) acc[j] = 0.f;
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iy = 2 * oy + ky, ix = 2 * ox + kx;
+                v[ci * 9 + ky * 3 + kx] = (iy < H && ix < W) ? __ldg(xb + ((long long)ci * H + iy) * W + ix) : 0.f;
+            }
+    float4 acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = f4zero();
+#pragma unroll
+    for (int tap = 0; tap < 27; ++tap) {
+        const float4 xv = make_float4(v[tap], v[tap], v[tap], v[tap]);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) acc[j] = f4fma(xv, *reinterpret_cast<const float4*>(&ws[tap * C0 + j * 4]), acc[j]);
+    }
+    float* zo = z + pix * C0;
+    float* yo = y + pix * C0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        st4(zo + j * 4, acc[j]);
+        const float4 u = f4fma(acc[j], *reinterpret_cast<const float4*>(&sc_s[j * 4]), *reinterpret_cast<const float4*>(&sh_s[j * 4]));
+        st4(yo + j * 4, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
+    }
+}
+
+constexpr int kStemP = 64;     // pixels staged per iteration
+
+// dW[co][tap] += sum_pixels x(tap) * dz[co].  Thread = (4-channel group cg, worker w): every worker walks its share
+// of the staged pixels with all 27 taps in registers (27 float4 accumulators): 1 vector + 27 broadcast scalar shared
+// loads feed 108 FMAs.  Reduction over workers through shared memory, then one round of atomics per CTA.
+template <int NV>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo) {
+    constexpr int C0 = NV * 4;
+    constexpr int NW = 256 / NV;                 // workers
+    __shared__ float xs[kStemP * 28];            // [pixel][27 taps (+1 pad)]
+    __shared__ __align__(16) float ds[kStemP * C0];
+    __shared__ float4 red[256];
+    const int t = threadIdx.x;
+    const int cg = t % NV, wk = t / NV;
+    const bool worker = wk < NW;
+    float4 acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = f4zero();
     const long long npix = (long long)B * Ho * Wo;
     for (long long p0 = (long long)blockIdx.x * kStemP; p0 < npix; p0 += (long long)gridDim.x * kStemP) {
         for (int i = t; i < kStemP * 27; i += 256) {
@@ -82,8 +139,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
             }
             xs[pp * 28 + tap] = v;
         }
-        for (int i = t; i < kStemP * C0 / 4; i += 256) {
-            const int pp = i / (C0 / 4), c4 = i - pp * (C0 / 4);
+        for (int i = t; i < kStemP * NV; i += 256) {
+            const int pp = i / NV, c4 = i - pp * NV;
             const long long pix = p0 + pp;
             float4 v = f4zero();
             if (pix < npix) v = ldg4(dz + pix * C0 + c4 * 4);
@@ -91,24 +148,28 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         }
         __syncthreads();
         if (worker) {
-#pragma unroll 4
-            for (int pp = 0; pp < kStemP; ++pp) {
-                const float g = ds[pp * C0 + co];
+            for (int pp = wk; pp < kStemP; pp += NW) {
+                const float4 g = *reinterpret_cast<const float4*>(&ds[pp * C0 + cg * 4]);
 #pragma unroll
-                for (int j = 0; j < kStemMaxI; ++j) {
-                    const int tap = ig + j * IG;
-                    if (tap < 27) acc[j] = fmaf(xs[pp * 28 + tap], g, acc[j]);
+                for (int tap = 0; tap < 27; ++tap) {
+                    const float xv = xs[pp * 28 + tap];
+                    acc[tap] = f4fma(make_float4(xv, xv, xv, xv), g, acc[tap]);
                 }
             }
         }
         __syncthreads();
     }
-    if (worker) {
 #pragma unroll
-        for (int j = 0; j < kStemMaxI; ++j) {
-            const int tap = ig + j * IG;
-            if (tap < 27) atomicAdd(dw + co * 27 + tap, acc[j]);
+    for (int tap = 0; tap < 27; ++tap) {
+        red[t] = worker ? acc[tap] : f4zero();
+        __syncthreads();
+        if (t < NV) {
+            float4 s = f4zero();
+            for (int k = 0; k < NW; ++k) s = f4add(s, red[k * NV + t]);
+            float* o = dw + (t * 4) * 27 + tap;           // dw[co][tap], co = 4*t + {0..3}
+            atomicAdd(o, s.x); atomicAdd(o + 27, s.y); atomicAdd(o + 54, s.z); atomicAdd(o + 81, s.w);
         }
+        __syncthreads();
     }
 }
 
@@ -124,23 +185,40 @@ extern "C" int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const f
     EFFDET_REQUIRE(aligned16(z) && aligned16(y) && aligned16(scale) && aligned16(shift), "stem_fwd: alignment");
     EFFDET_DEVICE(device);
     const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
-    const long long total = (long long)B * Ho * Wo * (C0 / 4);
-    stem_fwd_kernel<<<cdiv(total, 256), 256, 27 * C0 * sizeof(float), (cudaStream_t)stream>>>(
-        x_nchw, w_oihw, scale, shift, z, y, B, H, W, C0, Ho, Wo);
+    const long long npix = (long long)B * Ho * Wo;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C0) {      // stem widths of EfficientNet-B0..B7: 32, 32, 32, 40, 48, 48, 56, 64
+        case 32: stem_fwd_px_kernel<8><<<cdiv(npix, 128), 128, 0, st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, Ho, Wo); break;
+        case 40: stem_fwd_px_kernel<10><<<cdiv(npix, 128), 128, 0, st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, Ho, Wo); break;
+        case 48: stem_fwd_px_kernel<12><<<cdiv(npix, 128), 128, 0, st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, Ho, Wo); break;
+        case 56: stem_fwd_px_kernel<14><<<cdiv(npix, 128), 128, 0, st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, Ho, Wo); break;
+        case 64: stem_fwd_px_kernel<16><<<cdiv(npix, 128), 128, 0, st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, Ho, Wo); break;
+        default: {
+            const long long total = npix * (C0 / 4);
+            stem_fwd_kernel<<<cdiv(total, 256), 256, 27 * C0 * sizeof(float), st>>>(x_nchw, w_oihw, scale, shift, z, y, B, H, W, C0,
+                                                                                     Ho, Wo);
+        }
+    }
     return launch_status("stem_fwd_kernel");
 }
 
 extern "C" int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw_oihw, int B, int H, int W, int C0,
                                  int device, effdet_stream_t stream) {
     EFFDET_REQUIRE(x_nchw && dz && dw_oihw, "stem_wgrad: null tensor");
-    EFFDET_REQUIRE(C0 % 4 == 0 && C0 >= 8 && C0 <= 64, "stem_wgrad: C0=%d unsupported (8..64)", C0);
+    EFFDET_REQUIRE(C0 == 32 || C0 == 40 || C0 == 48 || C0 == 56 || C0 == 64, "stem_wgrad: C0=%d unsupported (32/40/48/56/64)", C0);
     EFFDET_REQUIRE(aligned16(dz), "stem_wgrad: alignment");
     EFFDET_DEVICE(device);
     const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
     const long long npix = (long long)B * Ho * Wo;
     int blocks = cdiv(npix, kStemP);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    const size_t smem = (size_t)kStemP * (28 + C0) * sizeof(float);
-    stem_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C0) {
+        case 32: stem_wgrad_kernel<8><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
+        case 40: stem_wgrad_kernel<10><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
+        case 48: stem_wgrad_kernel<12><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
+        case 56: stem_wgrad_kernel<14><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
+        default: stem_wgrad_kernel<16><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
+    }
     return launch_status("stem_wgrad_kernel");
 }
