@@ -104,24 +104,21 @@ __global__ void __launch_bounds__(128) stem_fwd_px_kernel(const float* __restric
 }
 
 constexpr int kStemP = 64;     // pixels staged per iteration
+constexpr int kStemMaxI = 7;   // taps per thread upper bound (27 / (256 / C0)) for C0 <= 64
 
-// dW[co][tap] += sum_pixels x(tap) * dz[co].  Thread = (4-channel group cg, worker w): every worker walks its share
-// of the staged pixels with all 27 taps in registers (27 float4 accumulators): 1 vector + 27 broadcast scalar shared
-// loads feed 108 FMAs.  Reduction over workers through shared memory, then one round of atomics per CTA.
-template <int NV>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
-                                                         float* __restrict__ dw, int B, int H, int W, int Ho, int Wo) {
-    constexpr int C0 = NV * 4;
-    constexpr int NW = 256 / NV;                 // workers
-    __shared__ float xs[kStemP * 28];            // [pixel][27 taps (+1 pad)]
-    __shared__ __align__(16) float ds[kStemP * C0];
-    __shared__ float4 red[256];
+                                                         float* __restrict__ dw, int B, int H, int W, int C0, int Ho,
+                                                         int Wo) {
+    extern __shared__ __align__(16) float sm[];
+    float* xs = sm;                    // [kStemP][28]  (27 taps, padded)
+    float* ds = sm + kStemP * 28;      // [kStemP][C0]
     const int t = threadIdx.x;
-    const int cg = t % NV, wk = t / NV;
-    const bool worker = wk < NW;
-    float4 acc[27];
+    const int IG = 256 / C0;           // tap groups
+    const int co = t % C0, ig = t / C0;
+    const bool worker = ig < IG;
+    float acc[kStemMaxI];
 #pragma unroll
-    for (int i = 0; i < 27; ++i) acc[i] = f4zero();
+    for (int j = 0; j < kStemMaxI; ++j) acc[j] = 0.f;
     const long long npix = (long long)B * Ho * Wo;
     for (long long p0 = (long long)blockIdx.x * kStemP; p0 < npix; p0 += (long long)gridDim.x * kStemP) {
         for (int i = t; i < kStemP * 27; i += 256) {
@@ -139,8 +136,8 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
             }
             xs[pp * 28 + tap] = v;
         }
-        for (int i = t; i < kStemP * NV; i += 256) {
-            const int pp = i / NV, c4 = i - pp * NV;
+        for (int i = t; i < kStemP * C0 / 4; i += 256) {
+            const int pp = i / (C0 / 4), c4 = i - pp * (C0 / 4);
             const long long pix = p0 + pp;
             float4 v = f4zero();
             if (pix < npix) v = ldg4(dz + pix * C0 + c4 * 4);
@@ -148,28 +145,24 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         }
         __syncthreads();
         if (worker) {
-            for (int pp = wk; pp < kStemP; pp += NW) {
-                const float4 g = *reinterpret_cast<const float4*>(&ds[pp * C0 + cg * 4]);
+#pragma unroll 4
+            for (int pp = 0; pp < kStemP; ++pp) {
+                const float g = ds[pp * C0 + co];
 #pragma unroll
-                for (int tap = 0; tap < 27; ++tap) {
-                    const float xv = xs[pp * 28 + tap];
-                    acc[tap] = f4fma(make_float4(xv, xv, xv, xv), g, acc[tap]);
+                for (int j = 0; j < kStemMaxI; ++j) {
+                    const int tap = ig + j * IG;
+                    if (tap < 27) acc[j] = fmaf(xs[pp * 28 + tap], g, acc[j]);
                 }
             }
         }
         __syncthreads();
     }
+    if (worker) {
 #pragma unroll
-    for (int tap = 0; tap < 27; ++tap) {
-        red[t] = worker ? acc[tap] : f4zero();
-        __syncthreads();
-        if (t < NV) {
-            float4 s = f4zero();
-            for (int k = 0; k < NW; ++k) s = f4add(s, red[k * NV + t]);
-            float* o = dw + (t * 4) * 27 + tap;           // dw[co][tap], co = 4*t + {0..3}
-            atomicAdd(o, s.x); atomicAdd(o + 27, s.y); atomicAdd(o + 54, s.z); atomicAdd(o + 81, s.w);
+        for (int j = 0; j < kStemMaxI; ++j) {
+            const int tap = ig + j * IG;
+            if (tap < 27) atomicAdd(dw + co * 27 + tap, acc[j]);
         }
-        __syncthreads();
     }
 }
 
@@ -205,20 +198,14 @@ extern "C" int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const f
 extern "C" int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw_oihw, int B, int H, int W, int C0,
                                  int device, effdet_stream_t stream) {
     EFFDET_REQUIRE(x_nchw && dz && dw_oihw, "stem_wgrad: null tensor");
-    EFFDET_REQUIRE(C0 == 32 || C0 == 40 || C0 == 48 || C0 == 56 || C0 == 64, "stem_wgrad: C0=%d unsupported (32/40/48/56/64)", C0);
+    EFFDET_REQUIRE(C0 % 4 == 0 && C0 >= 8 && C0 <= 64, "stem_wgrad: C0=%d unsupported (8..64)", C0);
     EFFDET_REQUIRE(aligned16(dz), "stem_wgrad: alignment");
     EFFDET_DEVICE(device);
     const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
     const long long npix = (long long)B * Ho * Wo;
     int blocks = cdiv(npix, kStemP);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (C0) {
-        case 32: stem_wgrad_kernel<8><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
-        case 40: stem_wgrad_kernel<10><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
-        case 48: stem_wgrad_kernel<12><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
-        case 56: stem_wgrad_kernel<14><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
-        default: stem_wgrad_kernel<16><<<blocks, 256, 0, st>>>(x_nchw, dz, dw_oihw, B, H, W, Ho, Wo); break;
-    }
+    const size_t smem = (size_t)kStemP * (28 + C0) * sizeof(float);
+    stem_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo);
     return launch_status("stem_wgrad_kernel");
 }
