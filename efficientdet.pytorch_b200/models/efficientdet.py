@@ -1,8 +1,12 @@
-"""``EfficientDet`` -- same constructor, attributes, call convention and state-dict schema as the
-reference's ``models/efficientdet.py``; everything under ``forward`` is sm_100a kernels.
+"""``EfficientDet`` -- the detector wrapper of the reference (``models/efficientdet.py``) as a thin host-side shell
+around sm_100a kernels.  Same constructor, attributes, call convention and state-dict schema:
 
-  train :  model([images[B,3,H,W], annotations[B,G,5]]) -> (cls_loss[1], reg_loss[1])   (:57-68)
-  eval  :  model(image[1,3,H,W]) -> [scores[K], classes[K] int64, boxes[K,4]]            (:69-86)
+  train :  model([images[B,3,H,W], annotations[B,G,5]]) -> (cls_loss[1], reg_loss[1])   (reference :57-68)
+  eval  :  model(image[1,3,H,W]) -> [scores[K], classes[K] int64, boxes[K,4]]            (reference :69-86)
+
+What differs underneath: features stay NHWC end to end, the head writes the level-concatenated
+``[B, sum(HWA), K]`` / ``[B, sum(HWA), 4]`` tensors directly (no ``torch.cat``), anchors are cached per input
+size, and decode + clip + threshold + NMS run on the device with two scalar read-backs.
 """
 import math
 
@@ -16,58 +20,78 @@ from .losses import FocalLoss
 from .module import Anchors, BBoxTransform, ClipBoxes
 from .retinahead import RetinaHead
 
+# detector name -> backbone name; d7 re-uses the b6 backbone like the reference table (:10-19)
 MODEL_MAP = {'efficientdet-d%d' % i: 'efficientnet-b%d' % min(i, 6) for i in range(8)}
+_PYRAMID_LEVELS = 5
+
+
+def _reference_reinit(model):
+    """The reference overwrites EVERY conv in the assembled model (backbone included) with
+    N(0, sqrt(2 / (k*k*out_channels))) and resets all BatchNorm affines to (1, 0) (reference :47-53)."""
+    for mod in model.modules():
+        if isinstance(mod, nn.Conv2d):
+            fan = mod.kernel_size[0] * mod.kernel_size[1] * mod.out_channels
+            mod.weight.data.normal_(0, math.sqrt(2. / fan))
+        elif isinstance(mod, nn.BatchNorm2d):
+            mod.weight.data.fill_(1)
+            mod.bias.data.zero_()
 
 
 class EfficientDet(nn.Module):
     def __init__(self, num_classes, network='efficientdet-d0', D_bifpn=3, W_bifpn=88, D_class=3, is_training=True,
                  threshold=0.01, iou_threshold=0.5):
         super().__init__()
-        self.backbone = EfficientNet.from_pretrained(MODEL_MAP[network])
+        # D_class is accepted and ignored, as in the reference (the head depth is fixed at 4 convs)
         self.is_training = is_training
-        self.neck = BIFPN(in_channels=self.backbone.get_list_features()[-5:], out_channels=W_bifpn,
-                          stack=D_bifpn, num_outs=5)
+        self.threshold, self.iou_threshold = threshold, iou_threshold
+        # registration order backbone -> neck -> bbox_head fixes the state-dict order
+        self.backbone = EfficientNet.from_pretrained(MODEL_MAP[network])
+        pyramid_channels = self.backbone.get_list_features()[-_PYRAMID_LEVELS:]
+        self.neck = BIFPN(in_channels=pyramid_channels, out_channels=W_bifpn, stack=D_bifpn, num_outs=_PYRAMID_LEVELS)
         self.bbox_head = RetinaHead(num_classes=num_classes, in_channels=W_bifpn)
         self.anchors = Anchors()
         self.regressBoxes = BBoxTransform()
         self.clipBoxes = ClipBoxes()
-        self.threshold = threshold
-        self.iou_threshold = iou_threshold
-        # the reference re-initialises every conv in the model, backbone included (:47-53)
-        for m in self.modules():
-            if isinstance(m, nn.Conv2d):
-                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
-                m.weight.data.normal_(0, math.sqrt(2. / n))
-            elif isinstance(m, nn.BatchNorm2d):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
+        _reference_reinit(self)
         self.freeze_bn()
         self.criterion = FocalLoss()
 
-    def forward(self, inputs):
-        if self.is_training:
-            inputs, annotations = inputs
-        feats = self.extract_feat_nhwc(inputs)
-        classification, regression = self.bbox_head.forward_concat_nhwc(feats)
-        anchors = self.anchors(inputs)
-        if self.is_training:
-            return self.criterion(classification, regression, anchors, annotations)
-        det = _ops.detect_image0(classification, regression, anchors, inputs.shape[2], inputs.shape[3],
-                                 self.threshold, self.iou_threshold)
-        if det is None:
-            print('No boxes to NMS')
-            return [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
-        return det
+    # -- feature extraction ---------------------------------------------------------------------------------
+    def extract_feat_nhwc(self, img):
+        stages = self.backbone.extract_features_nhwc(img)
+        return self.neck.forward_nhwc(stages[-_PYRAMID_LEVELS:])
+
+    def extract_feat(self, img):
+        """backbone + neck, returned as logical-NCHW views (reference :94-100)."""
+        return tuple(_ops.to_nchw_view(t) for t in self.extract_feat_nhwc(img))
 
     def freeze_bn(self):
-        """BatchNorm always runs on its running statistics (reference :88-92); here that is structural
-        -- BN is folded into the conv epilogues -- the call keeps the modules in eval mode for parity."""
+        """BatchNorm always runs on its running statistics (reference :88-92).  Here that is structural -- BN is
+        folded into the conv epilogues -- the call only keeps the holder modules in eval mode for parity."""
         for layer in self.modules():
             if isinstance(layer, nn.BatchNorm2d):
                 layer.eval()
 
-    def extract_feat_nhwc(self, img):
-        return self.neck.forward_nhwc(self.backbone.extract_features_nhwc(img)[-5:])
+    # -- the two call conventions -----------------------------------------------------------------------------
+    def _raw_predictions(self, images):
+        cls, reg = self.bbox_head.forward_concat_nhwc(self.extract_feat_nhwc(images))
+        return cls, reg, self.anchors(images)
 
-    def extract_feat(self, img):
-        return tuple(_ops.to_nchw_view(t) for t in self.extract_feat_nhwc(img))
+    def _losses(self, images, annotations):
+        cls, reg, anchors = self._raw_predictions(images)
+        return self.criterion(cls, reg, anchors, annotations)
+
+    def _detections(self, image):
+        cls, reg, anchors = self._raw_predictions(image)
+        found = _ops.detect_image0(cls, reg, anchors, image.shape[2], image.shape[3], self.threshold,
+                                   self.iou_threshold)
+        if found is None:
+            print('No boxes to NMS')
+            return [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
+        return found
+
+    def forward(self, inputs):
+        if self.is_training:
+            images, annotations = inputs
+            return self._losses(images, annotations)
+        return self._detections(inputs)
