@@ -87,3 +87,19 @@ def test_anchor_table_is_bit_exact_on_host():
     for (h, w) in [(512, 512), (384, 640), (1536, 1536)]:
         tab = _anchor_table(h, w, a.pyramid_levels, a.strides, a.sizes, a.ratios, a.scales)
         assert (tab == O.anchors_for(h, w)).all()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the contract keys."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'img/s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
