@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
 SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'stem.cu', 'depthwise.cu', 'mbconv_ops.cu', 'bifpn.cu', 'loss.cu',
-           'detect.cu', 'layout.cu']
+           'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -114,6 +114,8 @@ SIGNATURES = {
     'effdet_detect_candidates': [_P] * 8 + [_INT, _INT, _INT, _F, _F, _F] + _TAIL,
     'effdet_nms': [_P, _P, _INT, ctypes.c_double, _P, _P, _P] + _TAIL,
     'effdet_gather_detections': [_P, _P, _P, _P, _INT, _P, _P, _P] + _TAIL,
+    'effdet_multi_sumsq': [_P, _P, _P, _P, _INT, _INT, _P] + _TAIL,
+    'effdet_multi_clip_adamw': [_P] * 7 + [_INT, _INT, _P] + [_F] * 8 + [_INT] + _TAIL,
     'effdet_nchw_to_nhwc': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
     'effdet_nhwc_to_nchw': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
 }

@@ -248,6 +248,25 @@ int effdet_gather_detections(const float* boxes, const float* scores, const int3
                              float* out_boxes, int device, effdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * the optimizer step that follows backward in the reference loop,
+ *   clip_grad_norm_(parameters, max_norm) + AdamW.step()        (train.py:115-118, train.py:268)
+ * as two multi-tensor launches.  The tables live in DEVICE memory: per tensor t its fp32 data pointers and
+ * element count, per chunk c the tensor it belongs to and its element offset; one CTA per chunk.
+ *   effdet_multi_sumsq      : norm_sq[0] += sum_t sum_i g_t[i]^2
+ *   effdet_multi_clip_adamw : g *= min(1, max_norm/(sqrt(norm_sq)+1e-6)) (max_norm <= 0: no clipping);
+ *                             p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *                             p -= lr/bias_c1 * m / (sqrt(v)/sqrt(bias_c2) + eps)     (torch.optim.AdamW)
+ * ------------------------------------------------------------------------------------------ */
+int effdet_multi_sumsq(const uint64_t* g_ptrs, const int64_t* numels, const int32_t* chunk_tensor,
+                       const int64_t* chunk_off, int nchunks, int chunk, float* norm_sq, int device,
+                       effdet_stream_t stream);
+int effdet_multi_clip_adamw(const uint64_t* p_ptrs, const uint64_t* g_ptrs, const uint64_t* m_ptrs,
+                            const uint64_t* v_ptrs, const int64_t* numels, const int32_t* chunk_tensor,
+                            const int64_t* chunk_off, int nchunks, int chunk, const float* norm_sq, float max_norm,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, float bias_c1,
+                            float bias_c2, int write_clipped_grad, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout plumbing at the module boundary (callers see logical NCHW, kernels are NHWC).
  * ------------------------------------------------------------------------------------------ */
 int effdet_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, int device, effdet_stream_t stream);

@@ -606,3 +606,33 @@ def test_d7_1536_inference_vs_oracle():
     assert e_c < TOL and e_r < TOL
     n_ref = ref[0].numel()
     assert abs(det[0].numel() - n_ref) <= max(3, n_ref // 25)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused clip_grad_norm_ + AdamW vs torch's own implementations on the CPU
+# ------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('max_norm', [0.1, 1e9])
+def test_fused_clip_adamw_matches_torch(max_norm):
+    from models.fused_optim import FusedClipAdamW
+    g = torch.Generator().manual_seed(3)
+    shapes = [(1,), (7,), (33, 31), (256, 64, 3, 3), (65537,), (300001,), (16,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    dev_p = [torch.nn.Parameter(p.detach().clone().to(_dev())) for p in ref_p]
+    extra_ref = torch.nn.Parameter(torch.randn(5, generator=g))          # never receives a gradient (dead parameter)
+    extra_dev = torch.nn.Parameter(extra_ref.detach().clone().to(_dev()))
+    ref_opt = torch.optim.AdamW(ref_p + [extra_ref], lr=1e-2)
+    dev_opt = FusedClipAdamW(dev_p + [extra_dev], lr=1e-2, max_norm=max_norm)
+    for it in range(3):
+        for a, b in zip(ref_p, dev_p):
+            grad = torch.randn(a.shape, generator=g) * (0.5 + it)
+            a.grad = grad.clone()
+            b.grad = grad.clone().to(_dev())
+        total = torch.nn.utils.clip_grad_norm_(ref_p + [extra_ref], max_norm)
+        ref_opt.step()
+        dev_opt.step()
+        assert abs(float(dev_opt.last_norm_sq.sqrt()) - float(total)) <= 1e-5 * float(total)
+        for a, b in zip(ref_p, dev_p):
+            assert _rel(b.grad.cpu(), a.grad) < 5e-6          # gradients rescaled in place like clip_grad_norm_
+            assert _rel(b.detach().cpu(), a.detach()) < 5e-6, it
+    assert torch.equal(extra_dev.detach().cpu(), extra_ref.detach())
