@@ -757,9 +757,10 @@ class FocalLossFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 
 
-def detect_image0(cls, reg, anchors, img_h, img_w, threshold, iou_threshold):
-    """-> [scores[K], classes[K] int64, boxes[K,4]] for image 0, or None when nothing passes."""
-    cls0, reg0 = _contig(cls[0]), _contig(reg[0])
+def detect_image0(cls, reg, anchors, img_h, img_w, threshold, iou_threshold, index=0):
+    """-> [scores[K], classes[K] int64, boxes[K,4]] for image `index` (the reference only ever looks at image 0,
+    models/efficientdet.py:73-86), or None when nothing passes."""
+    cls0, reg0 = _contig(cls[index]), _contig(reg[index])
     A, K = cls0.shape
     anchors = _contig(anchors.view(-1, 4))
     npad = 1

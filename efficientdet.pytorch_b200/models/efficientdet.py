@@ -90,6 +90,24 @@ class EfficientDet(nn.Module):
             return [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
         return found
 
+    @torch.no_grad()
+    def detect_batch(self, images):
+        """Batched inference: one network pass over [B,3,H,W], then decode + threshold +
+        NMS per image.  The reference's forward only post-processes image 0 (models/efficientdet.py:73-86), which
+        is why eval.py feeds it one image at a time; entry i here equals forward(images[i:i+1]).
+        -> list of B triples [scores[K_i], classes[K_i] int64, boxes[K_i,4]] on the device (empty tensors when no
+        anchor passes the threshold)."""
+        cls, reg, anchors = self._raw_predictions(images)
+        out = []
+        for i in range(images.shape[0]):
+            found = _ops.detect_image0(cls, reg, anchors, images.shape[2], images.shape[3], self.threshold,
+                                       self.iou_threshold, index=i)
+            if found is None:
+                found = [cls.new_zeros(0), torch.zeros(0, dtype=torch.int64, device=cls.device),
+                         cls.new_zeros(0, 4)]
+            out.append(found)
+        return out
+
     def forward(self, inputs):
         if self.is_training:
             images, annotations = inputs

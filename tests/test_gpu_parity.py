@@ -636,3 +636,58 @@ def test_fused_clip_adamw_matches_torch(max_norm):
             assert _rel(b.grad.cpu(), a.grad) < 5e-6          # gradients rescaled in place like clip_grad_norm_
             assert _rel(b.detach().cpu(), a.detach()) < 5e-6, it
     assert torch.equal(extra_dev.detach().cpu(), extra_ref.detach())
+
+
+# ------------------------------------------------------------------------------------------------
+# batched inference = the reference's single-image post-processing applied per image
+# ------------------------------------------------------------------------------------------------
+
+def _match_rows(det, ref, tol_box, tol_score):
+    """order-insensitive count of reference detections (score, class, box) found in det"""
+    s, c, b = det
+    rs, rc, rb = ref
+    used, matched = np.zeros(s.shape[0], dtype=bool), 0
+    for j in range(rs.shape[0]):
+        dist = np.abs(b - rb[j]).sum(axis=1) + used * 1e9
+        k = int(np.argmin(dist)) if s.shape[0] else -1
+        if k >= 0 and dist[k] < tol_box and abs(s[k] - rs[j]) < tol_score and c[k] == rc[j]:
+            used[k] = True
+            matched += 1
+    return matched
+
+
+def test_detect_batch_matches_per_image_reference(prec):
+    cfg = O.make_config('efficientdet-d0', num_classes=20, W_bifpn=64, D_bifpn=2)
+    sd = O.init_state_dict(cfg, seed=61)
+    m = _build('efficientdet-d0', 20, 64, 2, sd, is_training=False)
+    m.eval()
+    images, _ = O.synthetic_batch(3, size=256, seed=62)
+    with torch.no_grad():
+        ocls, _, _ = O.raw_outputs(sd, images, cfg)
+    thr = float(torch.sort(ocls.max(dim=2)[0][0], descending=True)[0][400])
+    m.threshold, m.iou_threshold = thr, 0.5
+    x = images.to(_dev())
+    dets = m.detect_batch(x)
+    with torch.no_grad():
+        first = m(x)                                   # the reference API: image 0 of the same batch
+    assert len(dets) == 3
+    tol_box, tol_score = (1e-2, 1e-4) if prec == 'fp32' else (0.5, 1e-3)
+    # two passes over the same batch differ only by the order of the fp32 atomics of the SE mean
+    d0 = [t.cpu().numpy() for t in dets[0]]
+    f0 = [t.cpu().numpy() for t in first]
+    assert abs(d0[0].shape[0] - f0[0].shape[0]) <= 1
+    assert _match_rows(d0, f0, 1e-2, 1e-4) >= f0[0].shape[0] - 1
+    for i in range(3):
+        with torch.no_grad():
+            ref = [t.numpy() for t in O.detect(sd, images[i:i + 1], cfg, threshold=thr, iou_threshold=0.5)]
+        det = [t.cpu().numpy() for t in dets[i]]
+        assert dets[i][1].dtype == torch.int64 and det[2].shape[1:] == (4,)
+        n_ref, n = ref[0].shape[0], det[0].shape[0]
+        assert n_ref > 20 and abs(n - n_ref) <= 2, (i, n, n_ref)
+        matched = _match_rows(det, ref, tol_box, tol_score)
+        print('image', i, 'matched %d / %d (ours %d)' % (matched, n_ref, n))
+        assert matched >= n_ref - 2, (i, matched, n_ref)
+    # nothing above the threshold -> empty triples, as forward() returns for image 0
+    m.threshold = 2.0
+    for trip in m.detect_batch(x):
+        assert trip[0].numel() == 0 and trip[1].numel() == 0 and tuple(trip[2].shape) == (0, 4)
