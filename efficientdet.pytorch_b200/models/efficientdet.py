@@ -90,6 +90,14 @@ class EfficientDet(nn.Module):
             return [torch.zeros(0), torch.zeros(0), torch.zeros(0, 4)]
         return found
 
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """Accepts checkpoints written from a DistributedDataParallel-wrapped model as well: the reference's
+        `get_state_dict` (utils/helper.py:25-30) only unwraps DataParallel, so under DDP every key it saves carries
+        a `module.` prefix that `train.py:235` / `eval.py:374` then cannot load."""
+        if len(state_dict) and all(k.startswith('module.') for k in state_dict):
+            state_dict = {k[len('module.'):]: v for k, v in state_dict.items()}
+        return super().load_state_dict(state_dict, *args, **kwargs)
+
     @torch.no_grad()
     def detect_batch(self, images):
         """Batched inference: one network pass over [B,3,H,W], then decode + threshold +

@@ -24,11 +24,6 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self.last_norm_sq = None          # device scalar of the most recent step (read it only if you need it)
 
     def _table(self, gi, plist):
-        key = (gi, tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist))
-        hit = self._tables.get(gi)
-        if hit is not None and hit[0] == key:
-            return hit[1]
-        dev = plist[0].device
         ms, vs = [], []
         for p in plist:
             st = self.state[p]
@@ -38,6 +33,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.contiguous_format)
             ms.append(st['exp_avg'])
             vs.append(st['exp_avg_sq'])
+        # gradients are re-allocated by zero_grad(set_to_none=True) and the moments by load_state_dict():
+        # the device tables are rebuilt whenever any of the four pointers of any tensor moved
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), m.data_ptr(), v.data_ptr()) for p, m, v in zip(plist, ms, vs))
+        hit = self._tables.get(gi)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        dev = plist[0].device
         numels = np.array([p.numel() for p in plist], dtype=np.int64)
         ct, co = [], []
         for t, n in enumerate(numels):
@@ -81,7 +83,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
                    tab['co'].data_ptr(), tab['nchunks'], _CHUNK, norm_sq.data_ptr())
         for (gi, group, plist), tab in zip(live, tabs):
             st0 = self.state[plist[0]]
-            step = st0['step'] + 1
+            step = int(st0['step']) + 1          # int() also accepts the tensor step of a torch.optim.AdamW checkpoint
             for p in plist:
                 self.state[p]['step'] = step
             b1, b2 = group['betas']

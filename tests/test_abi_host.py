@@ -61,6 +61,21 @@ def test_state_dict_schema_matches_reference(net, W, D):
     assert m.backbone.get_list_features()[-5:] == cfg['stage_out'][-5:]
 
 
+def test_ddp_prefixed_checkpoint_loads():
+    """checkpoints saved from a DDP-wrapped model carry `module.` on every key (utils/helper.py:25-30 only
+    unwraps DataParallel); the drop-in model accepts both spellings, and still rejects foreign keys"""
+    from models import EfficientDet
+    cfg = O.make_config('efficientdet-d0', 20, 64, 2)
+    sd = O.init_state_dict(cfg, seed=5)
+    m = EfficientDet(num_classes=20, network='efficientdet-d0', D_bifpn=2, W_bifpn=64)
+    m.load_state_dict({'module.' + k: v for k, v in sd.items()})
+    got = m.state_dict()
+    assert list(got.keys()) == list(sd.keys())
+    assert all(torch.equal(got[k], sd[k]) for k in sd)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({'model.' + k: v for k, v in sd.items()})
+
+
 def test_no_cpu_fallback():
     from models import EfficientDet
     from models._native import EffdetNativeError
