@@ -649,7 +649,7 @@ class RetinaHeadFn(torch.autograd.Function):
             levels = []
             for lv, t in enumerate(acts[stacked]):
                 _, H, W, _ = t.shape
-                levels.append(dict(x_ptr=N.f32(t), x_bs=H * W * F, y_ptr=out.data_ptr() + 4 * offs[lv] * width,
+                levels.append(dict(x_ptr=N.f32(t), x_bs=H * W * F, y_ptr=N.f32(out) + 4 * offs[lv] * width,
                                    y_bs=tot * width, B=B, H=H, W=W))
             conv2d_multi_raw(feats[0], levels, wf, F, A * width, 3, bias=bias.detach(), act=act, w_tc=tc_packs(w)[0])
         ctx.meta = (nl, A, K, stacked, offs, tot)
@@ -683,7 +683,7 @@ class RetinaHeadFn(torch.autograd.Function):
             wl_levels = []
             for lv, t in enumerate(top):
                 _, H, W, _ = t.shape
-                dptr = dsrc.data_ptr() + 4 * offs[lv] * width
+                dptr = N.f32(dsrc) + 4 * offs[lv] * width
                 wl_levels.append(dict(x_ptr=N.f32(t), x_bs=H * W * F, dy_ptr=dptr, dy_bs=tot * width, B=B, H=H, W=W))
                 dl = _empty((B, H, W, F), t)
                 d.append(dl)
