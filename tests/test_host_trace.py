@@ -110,6 +110,78 @@ class Recorder:
                 self.need(a['dbias'], a['Cout'], name + ' dbias')
                 self.need(a['a_scale'], a['B'] * a['Cin'], name + ' a_scale')
                 assert (a['ws_x'] is None) == (a['precision'] == 0) and (a['ws_dy'] is None) == (a['precision'] == 0)
+        elif name in ('effdet_dwconv_fwd', 'effdet_dwconv_bwd_data', 'effdet_dwconv_bwd_weight'):
+            B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo = snap[-10:]
+            # Conv2dStaticSamePadding on even maps == TF-SAME (models/utils.py:126-155)
+            assert (k, stride) in ((3, 1), (3, 2), (5, 1), (5, 2))
+            assert (pad_t, pad_l) == {(3, 1): (1, 1), (3, 2): (0, 0), (5, 1): (2, 2), (5, 2): (1, 1)}[(k, stride)]
+            # the pads are STATIC (computed once for image_size 224), so the output size follows the conv formula,
+            # which equals ceil(H/stride) only on even maps
+            total = {(3, 1): 2, (3, 2): 1, (5, 1): 4, (5, 2): 3}[(k, stride)]
+            assert Ho == (H + total - k) // stride + 1 and Wo == (W + total - k) // stride + 1 and C % 4 == 0
+            big, small = B * H * W * C, B * Ho * Wo * C
+            if name == 'effdet_dwconv_fwd':
+                x, w, scale, shift, z, y = snap[:6]
+                self.need(x, big, 'dw x'); self.need(w, k * k * C, 'dw w')
+                self.need(scale, C, 'dw scale'); self.need(shift, C, 'dw shift')
+                self.need(z, small, 'dw z'); self.need(y, small, 'dw y')
+            elif name == 'effdet_dwconv_bwd_data':
+                dz, w, dx = snap[:3]
+                self.need(dz, small, 'dw dz'); self.need(w, k * k * C, 'dw w'); self.need(dx, big, 'dw dx')
+            else:
+                x, dz, dw = snap[:3]
+                self.need(x, big, 'dw x'); self.need(dz, small, 'dw dz'); self.need(dw, k * k * C, 'dw dw')
+        elif name == 'effdet_stem_fwd':
+            x, w, scale, shift, z, y, B, H, W, C0 = snap
+            assert H % 2 == 0 and W % 2 == 0
+            self.need(x, B * 3 * H * W, 'stem x'); self.need(w, C0 * 27, 'stem w')
+            self.need(scale, C0, 'stem scale'); self.need(shift, C0, 'stem shift')
+            self.need(z, B * (H // 2) * (W // 2) * C0, 'stem z'); self.need(y, B * (H // 2) * (W // 2) * C0, 'stem y')
+        elif name == 'effdet_stem_wgrad':
+            x, dz, dw, B, H, W, C0 = snap
+            self.need(x, B * 3 * H * W, 'stem x'); self.need(dz, B * (H // 2) * (W // 2) * C0, 'stem dz')
+            self.need(dw, C0 * 27, 'stem dw')
+        elif name == 'effdet_spatial_reduce':
+            a, b2, out, alpha, B, HW, C = snap
+            self.need(a, B * HW * C, 'reduce a'); self.need(b2, B * HW * C, 'reduce b2'); self.need(out, B * C, 'reduce out')
+        elif name == 'effdet_se_gate_fwd':
+            mean, w1, b1, w2, b2, s_pre, gate, B, C, S = snap
+            assert S >= 1
+            for p_, n_, w_ in ((mean, B * C, 'mean'), (w1, S * C, 'w1'), (b1, S, 'b1'), (w2, C * S, 'w2'), (b2, C, 'b2'),
+                               (s_pre, B * S, 's_pre'), (gate, B * C, 'gate')):
+                self.need(p_, n_, 'se_gate_fwd ' + w_)
+        elif name == 'effdet_se_gate_bwd':
+            dgate, mean, s_pre, gate, w1, w2, dmean, dw1, db1, dw2, db2, B, C, S = snap
+            for p_, n_, w_ in ((dgate, B * C, 'dgate'), (mean, B * C, 'mean'), (s_pre, B * S, 's_pre'), (gate, B * C, 'gate'),
+                               (w1, S * C, 'w1'), (w2, C * S, 'w2'), (dmean, B * C, 'dmean'), (dw1, S * C, 'dw1'),
+                               (db1, S, 'db1'), (dw2, C * S, 'dw2'), (db2, C, 'db2')):
+                self.need(p_, n_, 'se_gate_bwd ' + w_)
+        elif name == 'effdet_bnact_bwd':
+            a = snap[0]
+            n = a['B'] * a['HW'] * a['C']
+            for f in ('dy', 'z', 'dz'):
+                self.need(a[f], n, 'bnact_bwd ' + f)
+            for f in ('scale', 'shift', 'mean', 'rstd', 'dgamma', 'dbeta'):
+                self.need(a[f], a['C'], 'bnact_bwd ' + f)
+            self.need(a['row_scale'], a['B'], 'bnact_bwd row_scale')
+            self.need(a['gate'], a['B'] * a['C'], 'bnact_bwd gate')
+            self.need(a['dmean'], a['B'] * a['C'], 'bnact_bwd dmean')
+            assert a['dy'] is not None and a['z'] is not None and a['dz'] is not None
+        elif name in ('effdet_add', 'effdet_relu_bwd', 'effdet_sigmoid_bwd'):
+            for p_ in snap[:3]:
+                self.need(p_, snap[3], name)
+        elif name == 'effdet_bn_fold':
+            gamma, beta, mean, var, eps, scale, shift, rstd, C = snap
+            assert abs(eps - 1e-3) < 1e-9                     # models/utils.py:273-274
+            for p_ in (gamma, beta, mean, var, scale, shift, rstd):
+                self.need(p_, C, 'bn_fold')
+        elif name in ('effdet_focal_loss_fwd', 'effdet_focal_loss_bwd'):
+            B, A, K, G = snap[-6:-2]
+            assert (snap[-2], snap[-1]) == (0.25, 2.0)        # models/losses.py:33-34
+            self.need(snap[0], B * A * K, 'focal cls'); self.need(snap[1], B * A * 4, 'focal reg')
+            self.need(snap[2], A * 4, 'focal anchors'); self.need(snap[3], B * G * 5, 'focal annots')
+            if name == 'effdet_focal_loss_bwd':
+                self.need(snap[7], B * A * K, 'focal dcls'); self.need(snap[8], B * A * 4, 'focal dreg')
 
 
 def _struct_dict(s):
@@ -195,7 +267,7 @@ def test_scaled_variants_issue_consistent_geometry(traced, net, W, D, size):
     m.is_training = True
     m.freeze_bn()
     counts = []
-    for B, s in ((1, size), (2, size // 2)):
+    for B, s in ((1, size), (2, size - 128)):          # both multiples of 128, as the pyramid needs
         images, ann = O.synthetic_batch(B, size=s, num_classes=20, seed=4)
         for _ in range(2):
             for p in m.parameters():
