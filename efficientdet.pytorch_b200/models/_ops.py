@@ -495,6 +495,12 @@ class ConvBiasActFn(torch.autograd.Function):
 
 def _fuse_fwd(a, b, c, w, col, eps, mode):
     B, H, W, C = a.shape
+    # the reference fails with a shape mismatch in `w*in + w*F.interpolate(...)` (models/bifpn.py:188-201) when the
+    # pyramid does not halve exactly; the kernels index b as [y//2, x//2] / [2y+dy, 2x+dx], so refuse the same inputs
+    want = (B, H // 2, W // 2, C) if mode == FUSE_UP else (B, 2 * H, 2 * W, C)
+    if tuple(b.shape) != want or (mode == FUSE_UP and (H % 2 or W % 2)) or (c is not None and c.shape != a.shape):
+        raise N.EffdetNativeError('BiFPN levels must halve exactly (image height and width multiples of 128): node '
+                                  'input %s cannot be fused with %s' % (tuple(a.shape), tuple(b.shape)))
     out = torch.empty_like(a)
     wst = w.shape[1]
     args = N.FuseArgs(N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(out), B, H, W, C, mode)

@@ -283,3 +283,16 @@ def test_scaled_variants_issue_consistent_geometry(traced, net, W, D, size):
     assert c['effdet_dwconv_bwd_weight'] == nblocks and c['effdet_se_gate_bwd'] == nblocks
     assert c['effdet_bifpn_fuse_fwd'] == 8 * D and c['effdet_bifpn_fuse_bwd'] == 8 * D
     assert c['effdet_focal_loss_fwd'] == 1 and c['effdet_focal_loss_bwd'] == 1 and c['effdet_stem_wgrad'] == 1
+
+
+def test_non_halving_pyramid_is_refused(traced):
+    """192 = 1.5 * 128: P6 is 3x3 and P7 2x2 -- the reference dies with a shape mismatch inside BiFPNModule.forward
+    (models/bifpn.py:188-201); the drop-in must refuse too instead of letting the fusion kernel index out of range"""
+    rec, N = traced
+    from models import EfficientDet
+    cfg = O.make_config('efficientdet-d0', 20, 64, 2)
+    m = EfficientDet(num_classes=20, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=True)
+    m.load_state_dict(O.init_state_dict(cfg, seed=2))
+    images, ann = O.synthetic_batch(1, size=192, num_classes=20, seed=5)
+    with pytest.raises(N.EffdetNativeError, match='halve exactly'):
+        m([images, ann])
