@@ -16,6 +16,11 @@ from . import _native as N
 _CHUNK = 65536
 
 
+def _check_param(p):
+    if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+        raise N.EffdetNativeError('FusedClipAdamW needs contiguous CUDA float32 parameters and gradients')
+
+
 class FusedClipAdamW(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=0.1):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
@@ -67,8 +72,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             plist = [p for p in group['params'] if p.grad is not None]
             for p in plist:
-                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                    raise N.EffdetNativeError('FusedClipAdamW needs contiguous CUDA float32 parameters and gradients')
+                _check_param(p)
             if plist:
                 live.append((gi, group, plist))
         if not live:
@@ -92,5 +96,9 @@ class FusedClipAdamW(torch.optim.Optimizer):
                    tab['nchunks'], _CHUNK, norm_sq.data_ptr(), float(group['max_norm'] or 0.0), float(group['lr']),
                    float(b1), float(b2), float(group['eps']), float(group['weight_decay']), 1.0 - b1 ** step,
                    1.0 - b2 ** step, 1)
+            # the kernel wrote through raw pointers: tell autograd (and the packed-weight / folded-BN caches of
+            # models/_ops.py, which key on Tensor._version) that parameters and gradients changed in place
+            torch.autograd.graph.increment_version(plist)
+            torch.autograd.graph.increment_version([p.grad for p in plist])
         self.last_norm_sq = norm_sq
         return loss

@@ -296,3 +296,59 @@ def test_non_halving_pyramid_is_refused(traced):
     images, ann = O.synthetic_batch(1, size=192, num_classes=20, seed=5)
     with pytest.raises(N.EffdetNativeError, match='halve exactly'):
         m([images, ann])
+
+
+def test_parameter_updates_invalidate_the_packed_weight_caches(traced, monkeypatch):
+    """packed conv weights / folded BN are cached per parameter and keyed on (Tensor._version, data_ptr): a step
+    without an update re-uses them, an in-place update of ONE weight re-packs only that weight, and the fused
+    optimizer (whose kernel writes through raw pointers) must bump the versions itself so that EVERYTHING is
+    re-derived -- otherwise training would silently keep convolving with the initial weights"""
+    rec, N = traced
+    from models import EfficientDet
+    from models import fused_optim
+    monkeypatch.setattr(fused_optim, '_check_param', lambda p: None)
+    cfg = O.make_config('efficientdet-d0', 20, 64, 2)
+    m = EfficientDet(num_classes=20, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=True)
+    m.load_state_dict(O.init_state_dict(cfg, seed=2))
+    m.train()
+    m.is_training = True
+    m.freeze_bn()
+    images, ann = O.synthetic_batch(1, size=128, num_classes=20, seed=5)
+    derived = ('effdet_pack_conv_weight', 'effdet_pack_conv_weight_tc', 'effdet_pack_dw_weight', 'effdet_bn_fold')
+
+    def step(zero=True):
+        if zero:
+            for p in m.parameters():
+                p.grad = None
+        start = len(rec.calls)
+        cl, rl = m([images, ann])
+        (cl.mean() + rl.mean()).backward()
+        return collections.Counter(n for n, _ in rec.calls[start:] if n in derived)
+
+    cold = step()
+    # 31 backbone 1x1 (15 expand + 16 project) + 5 laterals + 16 BiFPN + 10 head convs; stem + 15 + 16 + 16 BatchNorms
+    assert cold == {'effdet_pack_conv_weight': 62, 'effdet_pack_conv_weight_tc': 62, 'effdet_pack_dw_weight': 16,
+                    'effdet_bn_fold': 48}
+    assert sum(step().values()) == 0                                   # warm: nothing re-derived
+    with torch.no_grad():
+        m.bbox_head.retina_cls.weight.mul_(1.0)                        # in-place update of one parameter
+    again = step()
+    assert again == {'effdet_pack_conv_weight': 1, 'effdet_pack_conv_weight_tc': 1}
+    with torch.no_grad():
+        m.backbone._bn0.weight.add_(0.0)
+    assert step() == {'effdet_bn_fold': 1}
+    # torch's own optimizer updates in place -> everything with a gradient is re-derived
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    opt.step()
+    after_torch = step()
+    # the fused optimizer must have the same effect
+    fused = fused_optim.FusedClipAdamW(m.parameters(), lr=1e-4, max_norm=0.1)
+    v0 = m.bbox_head.retina_cls.weight._version
+    g0 = m.bbox_head.retina_cls.weight.grad._version
+    fused.step()
+    assert m.bbox_head.retina_cls.weight._version > v0 and m.bbox_head.retina_cls.weight.grad._version > g0
+    names = [n for n, _ in rec.calls[-2:]]
+    assert names == ['effdet_multi_sumsq', 'effdet_multi_clip_adamw']
+    after_fused = step()
+    assert after_fused == after_torch
+    assert after_fused == cold                                          # every live parameter was re-derived
