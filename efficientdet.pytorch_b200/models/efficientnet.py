@@ -20,7 +20,14 @@ _VALID_NAMES = ['efficientnet-b%d' % i for i in range(8)]
 
 
 def _frozen_bn(bn):
-    """(gamma, beta, running_mean, running_var) of a holder BatchNorm2d, in kernel-argument order."""
+    """(gamma, beta, running_mean, running_var) of a holder BatchNorm2d, in kernel-argument order.
+    The kernels implement the frozen (running-statistics) BatchNorm the detector is trained with
+    (models/efficientdet.py:88-92, train.py:100-102); a BatchNorm left in batch-statistics mode would silently
+    compute something else than the reference, so it is refused."""
+    if bn.training:
+        raise _ops.N.EffdetNativeError(
+            'BatchNorm2d is in batch-statistics (training) mode; the B200 hot path implements the frozen BatchNorm '
+            'the reference trains with -- call freeze_bn() (or .eval()) after .train(), as train.py:100-102 does')
     return [bn.weight, bn.bias, bn.running_mean, bn.running_var]
 
 
@@ -149,6 +156,7 @@ class EfficientNet(nn.Module):
     def extract_features_nhwc(self, inputs):
         _ops.check_cuda_f32(inputs, 'EfficientNet input')
         stem_bn = self._bn0
+        _frozen_bn(stem_bn)
         x = _ops.StemFn.apply(inputs, self._conv_stem.weight, stem_bn.weight, stem_bn.bias, stem_bn.running_mean,
                               stem_bn.running_var, stem_bn.eps)
         total = len(self._blocks)

@@ -244,6 +244,9 @@ def test_drop_connect_uses_same_rng_stream():
     sd = O.init_state_dict(cfg, seed=12)
     m = _load(EfficientNet.from_name('efficientnet-b0'), sd, 'backbone.')
     m.train()
+    for mod in m.modules():                            # train.py:100-102: train() then freeze_bn()
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eval()
     x, _ = O.synthetic_batch(4, size=128, seed=4)
     torch.manual_seed(1234)
     outs = m(x.to(_dev()))

@@ -352,3 +352,18 @@ def test_parameter_updates_invalidate_the_packed_weight_caches(traced, monkeypat
     after_fused = step()
     assert after_fused == after_torch
     assert after_fused == cold                                          # every live parameter was re-derived
+
+
+def test_batch_statistics_batchnorm_is_refused(traced):
+    """model.train() WITHOUT freeze_bn() puts BatchNorm in batch-statistics mode: the reference would then normalise
+    with batch statistics, the kernels only implement the frozen BatchNorm -> refuse instead of diverging silently"""
+    rec, N = traced
+    from models import EfficientDet
+    m = EfficientDet(num_classes=20, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=True)
+    images, ann = O.synthetic_batch(1, size=128, num_classes=20, seed=5)
+    m([images, ann])                                  # as constructed: BN already frozen (models/efficientdet.py:55)
+    m.train()
+    with pytest.raises(N.EffdetNativeError, match='freeze_bn'):
+        m([images, ann])
+    m.freeze_bn()
+    m([images, ann])
