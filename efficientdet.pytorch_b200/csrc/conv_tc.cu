@@ -430,6 +430,318 @@ conv_tc_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL (round-2 staging, OFF unless EFFDET_B200_PAIR=1; not yet run on hardware):
+// CTA-pair variant of the multi-level kernel for Cout tiles of 256.  Two CTAs of a 2-cluster (one TPC) form one
+// tcgen05.mma.cta_group::2 tile of 256 pixels x 256 channels: each CTA gathers ITS 128 pixel rows of A and
+// stages only ITS 128-channel half of the weight tile, so a 64-channel k-block costs 32 KB (A) + 32 KB (B/2)
+// of L2->SM traffic per SM instead of 32 + 64 -- the weights were two thirds of the feed that caps the
+// single-CTA kernel at ~51 % tensor-pipe utilisation -- and three stages fit.
+// Protocol (after cutlass PipelineTmaUmmaAsync / SM100_TMA_2SM_LOAD / umma_arrive_multicast_2x1SM):
+//   * only the leader CTA (cluster rank 0) issues MMAs and owns the "full" barriers: its count is the
+//     8 gather warps of each CTA (the peer's arrive remotely) + the leader's TMA thread, which also posts
+//     the expected bytes of BOTH CTAs' weight halves; both TMA threads complete_tx on the leader's barrier;
+//   * "empty" and "accumulator ready" barriers exist in both CTAs at the same offset and are signalled by one
+//     multicast tcgen05.commit;
+//   * TMEM is allocated / freed by warp 8 of both CTAs with cta_group::2, bracketed by cluster barriers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// one commit, arrival on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMA tile -> this CTA's shared memory, bytes reported to the LEADER's mbarrier (shared::cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int STAGES>
+struct PairSmem {
+    static constexpr int kA = kTileM * 128;     // one bf16 plane of this CTA's 128 pixel rows
+    static constexpr int kB = 128 * 128;        // one bf16 plane of this CTA's 128-channel half of the weight tile
+    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kChan = 256 * 4;       // bias of the pair's 256 output channels
+    static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kChan;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+conv_tc_pair_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks) {
+    using S = PairSmem<STAGES>;
+    constexpr int BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [256] bias
+
+    // geometry of THIS CTA's 128 pixel rows (the two CTAs of a pair may sit on different pyramid levels: the
+    // weights are shared by all levels, only the gather and the output addressing are per CTA)
+    const int tile = blockIdx.x;
+    int l = 0;
+    while (l + 1 < ma.nlevels && tile >= ma.tile_begin[l + 1]) ++l;
+    const effdet_conv_args& p = ma.lv[l];
+    const bool dummy = tile >= ma.tile_begin[ma.nlevels];           // grid padded to an even number of tiles
+    const int M = dummy ? 0 : p.B * p.H * p.W, HW = p.H * p.W;
+    const int m0 = dummy ? 0 : (tile - ma.tile_begin[l]) * kTileM;
+    const int n0 = blockIdx.y * BN;
+
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
+    const int KT = taps * kblocks;
+    for (int i = threadIdx.x; i < BN; i += kFwdThreads) {
+        const int n = n0 + i;
+        chan[i] = (n < p.Cout && p.bias) ? __ldg(p.bias + n) : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 8 + 8 + 1);        // gather warps of both CTAs + the leader's TMA thread (leader's copy only is used)
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc_pair<BN>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();                                // barriers of both CTAs initialised, TMEM allocated on both SMs
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t leader_full0 = mapa_cluster(smem_u32(&full_bar[0]), 0);      // stage s: + 8 * s
+
+    if (warp < 8) {
+        // ---------------- producers: im2col gather of this CTA's 128 rows + bf16 split -----------------
+        const int t = threadIdx.x;
+        const int j = t & 7;
+        long long base[4];
+        int oyx[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 32 + (t >> 3);
+            const int m = m0 + r;
+            if (m < M) {
+                const int b = m / HW;
+                const int pix = m - b * HW;
+                const int oy = pix / p.W;
+                oyx[i] = (oy << 16) | (pix - oy * p.W);
+                base[i] = (long long)b * p.x_bstride;
+            } else {
+                oyx[i] = -1;
+                base[i] = 0;
+            }
+        }
+        auto load_stage = [&](int kt, float4 (&v)[8]) {
+            const int tap = kt / kblocks;
+            const int c = (kt - tap * kblocks) * kTileK + j * 8;
+            const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[2 * i] = f4zero();
+                v[2 * i + 1] = f4zero();
+                if (oyx[i] >= 0 && c < p.Cin) {
+                    const int iy = (oyx[i] >> 16) + ky, ix = (oyx[i] & 0xffff) + kx;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                        const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
+                        v[2 * i] = ldg4(src);
+                        if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
+                    }
+                }
+            }
+        };
+        auto store_stage = [&](int kt, const float4 (&v)[8]) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+            uint8_t* a_hi = smem + s * S::kStage;
+            uint8_t* a_lo = a_hi + S::kA;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 32 + (t >> 3);
+                uint4 hi, lo;
+                split8(v[2 * i], v[2 * i + 1], hi, lo);
+                const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                *reinterpret_cast<uint4*>(a_lo + off) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_full0 + 8 * s);
+        };
+        float4 va[8], vb[8];
+        load_stage(0, va);
+        for (int kt = 0; kt < KT; kt += 2) {
+            if (kt + 1 < KT) load_stage(kt + 1, vb);
+            store_stage(kt, va);
+            if (kt + 1 < KT) {
+                if (kt + 2 < KT) load_stage(kt + 2, va);
+                store_stage(kt + 1, vb);
+            }
+        }
+        // ---------------- epilogue: this CTA's 128 rows x 256 channels ---------------------------------
+        mbar_wait_cluster(accum_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3, half = warp >> 2;
+        const int m = m0 + quarter * 32 + lane;
+        const bool row_ok = m < M;
+        int b = 0;
+        long long pix = 0;
+        if (row_ok) {
+            b = m / HW;
+            pix = m - b * HW;
+        }
+        const int ncols = min(BN, p.Cout - n0);
+        const int nchunks = (ncols + 31) >> 5;
+        const int c_begin = half ? (nchunks + 1) >> 1 : 0, c_end = half ? nchunks : (nchunks + 1) >> 1;
+        const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
+        const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
+        const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
+#pragma unroll 1
+        for (int cc = c_begin; cc < c_end; ++cc) {
+            uint32_t acc[32];
+            tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
+            float4 rv[8], mv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int n = n0 + cc * 32 + q * 4;
+                rv[q] = f4zero();
+                mv[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (row_ok && n < p.Cout) {
+                    if (p.residual) rv[q] = ldg4(p.residual + rbase + n);
+                    if (p.mask_src) mv[q] = ldg4(p.mask_src + mbase + n);
+                }
+            }
+            tmem_ld32_wait(acc);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int nl = cc * 32 + q * 4;
+                const int n = n0 + nl;
+                if (n >= p.Cout) break;
+                float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
+                                       __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
+                v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
+                if (p.act == EFFDET_ACT_RELU) {
+                    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+                } else if (p.act == EFFDET_ACT_SIGMOID) {
+                    v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+                } else if (p.act == EFFDET_ACT_SWISH) {
+                    v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+                }
+                v = f4add(v, rv[q]);
+                if (p.mask_src)
+                    v = make_float4(mv[q].x > 0.f ? v.x : 0.f, mv[q].y > 0.f ? v.y : 0.f, mv[q].z > 0.f ? v.z : 0.f,
+                                    mv[q].w > 0.f ? v.w : 0.f);
+                st4(p.y + ybase + n, v);
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 8) {
+        // ---------------- TMA: this CTA's 128-channel half of the weight tile (hi plane, lo plane) ------
+        if (lane == 0) {
+            const int nhalf = n0 + (int)rank * 128;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+                uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
+                const uint32_t bar = leader_full0 + 8 * s;
+                if (leader) mbar_arrive_expect_tx_cluster(bar, 4 * S::kB);      // both halves, both planes
+                tma_load_3d_pair(b_hi, &wmap, bar, kt * kTileK, nhalf, 0);
+                tma_load_3d_pair(b_hi + S::kB, &wmap, bar, kt * kTileK, nhalf, 1);
+            }
+        }
+    } else {
+        // ---------------- MMA issue: leader CTA only, M = 256 over the pair -----------------------------
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(2 * kTileM, BN, 0, 0);
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                mbar_wait_cluster(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k) {
+                    const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
+                    const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024), dbl = umma_desc(b_lo + k * 32, 16, 1024);
+                    umma_bf16_pair(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16_pair(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16_pair(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit_pair(&empty_bar[s], 3);
+            }
+            umma_commit_pair(accum_bar, 3);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                // nobody frees TMEM / exits while the pair still works
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc_pair<BN>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight-gradient kernel:  D[n, c | tap] += sum_pixels dy[pixel, n] * x[pixel + tap, c]
 //   GEMM-M = 128 output channels, GEMM-N = BC input channels, GEMM-K = pixels (64 per stage);
 //   both operands are NHWC rows (channels contiguous) = MN-major SWIZZLE_128B operands:
@@ -1060,6 +1372,15 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g);
 
+// round-2 staging switch: the CTA-pair kernel has been compiled but never run on hardware -> opt-in only
+static bool pair_enabled() {
+    static const bool on = [] {
+        const char* v = getenv("EFFDET_B200_PAIR");
+        return v && v[0] == '1';
+    }();
+    return on;
+}
+
 int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(EFFDET_ERR_UNSUPPORTED, "conv2d_multi(tc): cuTensorMapEncodeTiled unavailable");
@@ -1087,6 +1408,21 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
         tiles += cdiv((long long)levels[l].B * levels[l].H * levels[l].W, kTileM);
     }
     for (int l = nlevels; l <= kMaxLevels; ++l) ma.tile_begin[l] = tiles;
+    if (BN == 256 && pair_enabled()) {
+        // experimental CTA-pair kernel: same tiles, grid padded to whole pairs, weight box = one 128-channel half
+        CUtensorMap hmap;
+        const cuuint32_t hbox[3] = {(cuuint32_t)kTileK, 128, 1};
+        r = enc(&hmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_tc), gdim, gstr, hbox, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc pair): cuTensorMapEncodeTiled failed (%d)", (int)r);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_multi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PairSmem<3>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc pair): smem opt-in: %s", cudaGetErrorString(e));
+        dim3 pgrid((tiles + 1) / 2 * 2, cdiv(a->Cout, 256));
+        conv_tc_pair_multi_kernel<3><<<pgrid, kFwdThreads, PairSmem<3>::kBytes, st>>>(hmap, ma, kblocks);
+        return launch_status("conv_tc_pair_multi_kernel");
+    }
     dim3 grid(tiles, cdiv(a->Cout, BN));
 #define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
     do {                                                                                                                  \
