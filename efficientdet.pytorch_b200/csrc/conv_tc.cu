@@ -734,6 +734,7 @@ conv_tc_pair_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid
         }
     }
     tc_fence_before();
+    __syncwarp();                                      // lanes 1..31 of the TMA / MMA warps rejoin lane 0 before the aligned barrier
     cluster_sync_all();                                // nobody frees TMEM / exits while the pair still works
     if (warp == 8) {
         tc_fence_after();
