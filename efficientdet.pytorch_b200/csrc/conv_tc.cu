@@ -1182,6 +1182,162 @@ wgrad_tc2_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constan
     }
 }
 
+// EXPERIMENTAL (round-2 staging, OFF unless EFFDET_B200_PAIR=1; not yet run on hardware): CTA-pair variant of
+// wgrad_tc2_multi_kernel<256>.  One cta_group::2 tile = 256 output channels x 256 input channels; CTA r of the pair
+// stages the dy planes of ITS 128 output channels (rows of D) and the x planes of ITS 128 input channels (half of the
+// N operand), i.e. 64 KB per 64-pixel stage instead of 96 KB, three stages.  Barrier protocol as in
+// conv_tc_pair_multi_kernel; everything is TMA-fed, so the leader's "full" barrier has a single arrival.
+__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+template <int STAGES>
+struct WgPairSmem {
+    static constexpr int kA = kTileK * 128 * 2;     // one plane of this CTA's dy tile: 2 groups of 64 output channels
+    static constexpr int kB = kTileK * 128 * 2;     // one plane of this CTA's x half: 2 groups of 64 input channels
+    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kBytes = STAGES * kStage + 1024 + 256;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+wgrad_tc2_pair_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgMultiArgs a, const int chunks_per_split,
+                            const int ctiles) {
+    using S = WgPairSmem<STAGES>;
+    constexpr int BC = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pairid = blockIdx.x >> 1;
+    const int ct = pairid % ctiles, nt = pairid / ctiles;
+    const int c0 = ct * BC;                                // the pair's 256 input channels (columns of D)
+    const int n0 = nt * 2 * kTileM + (int)rank * kTileM;   // this CTA's 128 output channels (rows of D)
+    const int chalf = c0 + (int)rank * 128;                // this CTA's half of the N operand
+    const int tap = blockIdx.y;
+    const int pad = a.ksize / 2;
+    const int dy = tap / a.ksize - pad, dx = tap % a.ksize - pad;
+    const int nchunks = a.chunk_begin[a.nlevels];
+    const int ch_begin = blockIdx.z * chunks_per_split;
+    const int ch_end = min(nchunks, ch_begin + chunks_per_split);
+    const int KT = ch_end - ch_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc_pair<BC>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t leader_full0 = mapa_cluster(smem_u32(&full_bar[0]), 0);
+    constexpr int GROUP = kTileK * 128;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int l = 0;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                const int chg = ch_begin + kt;
+                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
+                const WgGeom& g = a.g[l];
+                int ch = chg - a.chunk_begin[l];
+                const int bx = ch % g.nbx;
+                ch /= g.nbx;
+                const int by = ch % g.nby;
+                const int bb = ch / g.nby;
+                const int x0 = bx * g.Wb, y0 = by * g.Hb, b0 = bb * g.Bb;
+                const uint32_t bytes_cta = (uint32_t)(2 * (2 + 2) * g.kstage * 128);
+                mbar_wait_cluster(&empty_bar[s], ph ^ 1);
+                const uint32_t bar = leader_full0 + 8 * s;
+                if (leader) mbar_arrive_expect_tx_cluster(bar, 2 * bytes_cta);
+                uint8_t* a_hi = smem + s * S::kStage;
+                uint8_t* b_hi = a_hi + 2 * S::kA;
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        tma_load_5d_pair(a_hi + pl * S::kA + q * GROUP, &maps.dy[l], bar, n0 + q * 64, x0, y0, b0, pl);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        tma_load_5d_pair(b_hi + pl * S::kB + q * GROUP, &maps.x[l], bar, chalf + q * 64, x0 + dx, y0 + dy, b0, pl);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(2 * kTileM, BC, 1, 1);
+            constexpr uint32_t LBO = GROUP, SBO = 1024;
+            int l = 0;
+            for (int kt = 0; kt < KT; ++kt) {
+                const int s = kt % STAGES;
+                const uint32_t ph = (kt / STAGES) & 1;
+                const int chg = ch_begin + kt;
+                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
+                const int ksteps = a.g[l].kstage / 16;
+                mbar_wait_cluster(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                const uint32_t a_lo = a_hi + S::kA;
+                const uint32_t b_hi = a_hi + 2 * S::kA;
+                const uint32_t b_lo = b_hi + S::kB;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t ko = k * 2 * SBO;
+                    const uint64_t dah = umma_desc(a_hi + ko, LBO, SBO), dal = umma_desc(a_lo + ko, LBO, SBO);
+                    const uint64_t dbh = umma_desc(b_hi + ko, LBO, SBO), dbl = umma_desc(b_lo + ko, LBO, SBO);
+                    umma_bf16_pair(tmem_base, dal, dbh, idesc, (kt | k) != 0);
+                    umma_bf16_pair(tmem_base, dah, dbl, idesc, 1);
+                    umma_bf16_pair(tmem_base, dah, dbh, idesc, 1);
+                }
+                umma_commit_pair(&empty_bar[s], 3);
+            }
+            umma_commit_pair(accum_bar, 3);
+        }
+    } else {
+        if (KT > 0) {
+            mbar_wait_cluster(accum_bar, 0);
+            tc_fence_after();
+            const int n = n0 + warp * 32 + lane;
+            const int kk = a.ksize * a.ksize;
+#pragma unroll 1
+            for (int cc = 0; cc < BC / 32; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
+                if (n >= a.Cout) continue;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int c = c0 + cc * 32 + q;
+                    if (c < a.Cin) atomicAdd(a.dw + ((long long)n * a.Cin + c) * kk + tap, __uint_as_float(acc[q]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc_pair<BC>(tmem_base);
+    }
+}
+
 // fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ a_scale,
                                                            __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad) {
@@ -1558,8 +1714,22 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     if (splits > cdiv(chunks, 4)) splits = cdiv(chunks, 4);
     int cps = cdiv(chunks, splits);
     splits = cdiv(chunks, cps);
-    dim3 grid(ctiles * ntiles, taps, splits);
     cudaError_t e;
+    if (BC == 256 && a0->Cout >= 256 && pair_enabled()) {
+        // experimental CTA-pair kernel: 256 x 256 tiles of the weight gradient per cluster of two CTAs
+        constexpr int ST = 3;
+        const int npairs = ctiles * cdiv(a0->Cout, 2 * kTileM);
+        int ps = (148 * 2) / (npairs * 2 * taps);
+        if (ps < 1) ps = 1;
+        if (ps > cdiv(chunks, 4)) ps = cdiv(chunks, 4);
+        const int pcps = cdiv(chunks, ps);
+        ps = cdiv(chunks, pcps);
+        e = cudaFuncSetAttribute(wgrad_tc2_pair_multi_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgPairSmem<ST>::kBytes);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad_multi(tc pair): smem opt-in: %s", cudaGetErrorString(e));
+        wgrad_tc2_pair_multi_kernel<ST><<<dim3(npairs * 2, taps, ps), kTcThreads, WgPairSmem<ST>::kBytes, st>>>(maps, ma, pcps, ctiles);
+        return launch_status("wgrad_tc2_pair_multi_kernel");
+    }
+    dim3 grid(ctiles * ntiles, taps, splits);
     if (BC == 256) {
         constexpr int ST = 2;
         e = cudaFuncSetAttribute(wgrad_tc2_multi_kernel<256, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<256, ST>::kBytes);
