@@ -297,7 +297,7 @@ def run_ours(args):
                         traffic=dict(per_launch_bytes=223.0e6, algorithmic_bytes=268.4e6,
                                      source='ncu --set full, P3 256->256 launch: dram read 136.8 MB + write 86.2 MB '
                                             '(profiles/r01_ncu_conv_tc_kernel_p3.txt)') if tc else None)
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # the CPU leg is an N=1 measurement (the host cores are shared by all ranks)
             cores = usable_cores()
             ips, dt = cpu_reference_steps(4, 2, 1, cores)
             cpu_base = dict(value=round(ips, 3), unit='img/s', cores=cores, kind='port',
