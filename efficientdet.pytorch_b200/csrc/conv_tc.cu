@@ -180,7 +180,10 @@ struct FwdSmem {
 };
 
 // MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
-template <int BN, int STAGES, bool MB>
+// COAL = true (EXPERIMENTAL, round-2 staging, opt-in with EFFDET_B200_COAL=1, not yet run on hardware) replaces the
+// epilogue's thread-per-row global accesses (32 rows x 16 B per warp instruction = 32 half-filled sectors) by a
+// per-warp shared-memory transpose so that every warp instruction reads / writes 4 rows x 128 contiguous bytes.
+template <int BN, int STAGES, bool MB, bool COAL = false>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effdet_conv_args& p, const int M, const int HW,
                                              const int kblocks, const int m0, const int n0) {
     using S = FwdSmem<BN, STAGES>;
@@ -308,6 +311,67 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
         const int ncols = min(BN, p.Cout - n0);
         const int nchunks = (ncols + 31) >> 5;
         const int c_begin = half ? (nchunks + 1) >> 1 : 0, c_end = half ? nchunks : (nchunks + 1) >> 1;
+        if constexpr (COAL) {
+            // every MMA has completed (accum_bar), so the stage buffers are free: [0,1024) image / pixel index of the
+            // CTA's 128 rows, then one 32 x 36-float transpose tile per warp (36: 16-byte aligned rows, and both the
+            // row-wise float4 writes and the transposed float4 reads are bank-conflict free per quarter warp)
+            int2* rowinfo = reinterpret_cast<int2*>(smem);
+            float* T = reinterpret_cast<float*>(smem + 1024) + warp * (32 * 36);
+            static_assert(1024 + 8 * 32 * 36 * 4 <= S::kStage, "transpose tiles must fit in one stage");
+            rowinfo[quarter * 32 + lane] = make_int2(row_ok ? b : -1, (int)pix);
+            __syncwarp();
+            const int colq = (lane & 7) * 4;
+#pragma unroll 1
+            for (int cc = c_begin; cc < c_end; ++cc) {
+                uint32_t acc[32];
+                tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
+                const int nl = cc * 32 + colq;
+                const int n = n0 + nl;
+                float4 rv[8], mv[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int2 ri = rowinfo[quarter * 32 + it * 4 + (lane >> 3)];
+                    rv[it] = f4zero();
+                    mv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (ri.x >= 0 && n < p.Cout) {
+                        if (p.residual) rv[it] = ldg4(p.residual + (long long)ri.x * p.r_bstride + (long long)ri.y * p.Cout + n);
+                        if (p.mask_src) mv[it] = ldg4(p.mask_src + (long long)ri.x * p.m_bstride + (long long)ri.y * p.Cout + n);
+                    }
+                }
+                tmem_ld32_wait(acc);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(T + lane * 36 + q * 4) =
+                        make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]), __uint_as_float(acc[q * 4 + 2]),
+                                    __uint_as_float(acc[q * 4 + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = it * 4 + (lane >> 3);
+                    const int2 ri = rowinfo[quarter * 32 + row];
+                    if (ri.x < 0 || n >= p.Cout) continue;
+                    float4 v = *reinterpret_cast<const float4*>(T + row * 36 + colq);
+                    v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
+                    const long long yb = (long long)ri.x * p.y_bstride + (long long)ri.y * p.Cout + n;
+                    if (MB && p.z) st4(p.z + yb, v);
+                    if (MB) v = f4fma(v, *reinterpret_cast<const float4*>(chan + BN + nl), *reinterpret_cast<const float4*>(chan + 2 * BN + nl));
+                    if (p.act == EFFDET_ACT_RELU) {
+                        v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+                    } else if (p.act == EFFDET_ACT_SIGMOID) {
+                        v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+                    } else if (p.act == EFFDET_ACT_SWISH) {
+                        v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+                    }
+                    if (MB && p.row_scale) v = f4scale(v, __ldg(p.row_scale + ri.x));
+                    v = f4add(v, rv[it]);
+                    if (p.mask_src)
+                        v = make_float4(mv[it].x > 0.f ? v.x : 0.f, mv[it].y > 0.f ? v.y : 0.f, mv[it].z > 0.f ? v.z : 0.f,
+                                        mv[it].w > 0.f ? v.w : 0.f);
+                    st4(p.y + yb, v);
+                }
+                __syncwarp();                          // the next chunk overwrites T
+            }
+        } else {
         const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
         const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
         const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
@@ -354,6 +418,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
                 st4(p.y + ybase + n, v);
             }
         }
+        }   // !COAL
         tc_fence_before();
     } else if (warp == 8) {
         // ---------------- TMA: weight tiles (hi plane, lo plane) ---------------------------------------
@@ -401,11 +466,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
     }
 }
 
-template <int BN, int STAGES, bool MB>
+template <int BN, int STAGES, bool MB, bool COAL = false>
 __global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ effdet_conv_args p, const int M, const int HW,
                const int kblocks) {
-    conv_tc_body<BN, STAGES, MB>(wmap, p, M, HW, kblocks, blockIdx.x * kTileM, blockIdx.y * BN);
+    conv_tc_body<BN, STAGES, MB, COAL>(wmap, p, M, HW, kblocks, blockIdx.x * kTileM, blockIdx.y * BN);
 }
 
 // Several pyramid levels that share one weight tensor (RetinaHead runs the same convs on P3..P7,
@@ -418,14 +483,14 @@ struct ConvMultiArgs {
     int nlevels;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool COAL = false>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_tc_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks) {
     const int tile = blockIdx.x;
     int l = 0;
     while (l + 1 < ma.nlevels && tile >= ma.tile_begin[l + 1]) ++l;
     const effdet_conv_args& p = ma.lv[l];
-    conv_tc_body<BN, STAGES, false>(wmap, p, p.B * p.H * p.W, p.H * p.W, kblocks, (tile - ma.tile_begin[l]) * kTileM,
+    conv_tc_body<BN, STAGES, false, COAL>(wmap, p, p.B * p.H * p.W, p.H * p.W, kblocks, (tile - ma.tile_begin[l]) * kTileM,
                                     blockIdx.y * BN);
 }
 
@@ -1471,6 +1536,16 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 
 
+// round-2 staging switches: compiled, never run on hardware -> opt-in only
+static bool env_flag(const char* name) {
+    const char* v = getenv(name);
+    return v && v[0] == '1';
+}
+static bool coalesced_epilogue_enabled() {
+    static const bool on = env_flag("EFFDET_B200_COAL");
+    return on;
+}
+
 bool conv_tc_eligible(const effdet_conv_args* a) {
     if (a->w_tc == nullptr || a->Cin % 4 || a->Cout % 4 || a->Cout < 16) return false;
     // measured (profiles/r01_bench_full_breakdown.json): the narrowest 1x1 layers are faster on the CUDA cores
@@ -1499,17 +1574,23 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
     dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
     const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
-#define EFFDET_TC_LAUNCH1(BN_, ST_, MB_)                                                                                   \
+    const bool coal = coalesced_epilogue_enabled();
+#define EFFDET_TC_LAUNCH1(BN_, ST_, MB_, CO_)                                                                              \
     do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
-        conv_tc_kernel<BN_, ST_, MB_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
+        conv_tc_kernel<BN_, ST_, MB_, CO_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks); \
     } while (0)
 #define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
     do {                                                                                                                  \
-        if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true);                                                                        \
-        else EFFDET_TC_LAUNCH1(BN_, ST_, false);                                                                          \
+        if (coal) {                                                                                                       \
+            if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true, true);                                                              \
+            else EFFDET_TC_LAUNCH1(BN_, ST_, false, true);                                                                \
+        } else {                                                                                                          \
+            if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true, false);                                                             \
+            else EFFDET_TC_LAUNCH1(BN_, ST_, false, false);                                                               \
+        }                                                                                                                 \
     } while (0)
     // short reductions (1x1 convs of the backbone): single-stage instances so 2-3 CTAs share an SM and hide each
     // other's prologue / epilogue; long reductions: deep pipelines, one CTA per SM
@@ -1581,16 +1662,22 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
         return launch_status("conv_tc_pair_multi_kernel");
     }
     dim3 grid(tiles, cdiv(a->Cout, BN));
-#define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
+#define EFFDET_TCM_LAUNCH1(BN_, ST_, CO_)                                                                                  \
     do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_multi_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_multi_kernel<BN_, ST_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): smem opt-in: %s", cudaGetErrorString(e)); \
-        conv_tc_multi_kernel<BN_, ST_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks);           \
+        conv_tc_multi_kernel<BN_, ST_, CO_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks);      \
+    } while (0)
+#define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
+    do {                                                                                                                  \
+        if (coalesced_epilogue_enabled()) EFFDET_TCM_LAUNCH1(BN_, ST_, true);                                             \
+        else EFFDET_TCM_LAUNCH1(BN_, ST_, false);                                                                         \
     } while (0)
     if (BN == 64) EFFDET_TCM_LAUNCH(64, 4);
     else if (BN == 128) EFFDET_TCM_LAUNCH(128, 3);
     else EFFDET_TCM_LAUNCH(256, 2);
+#undef EFFDET_TCM_LAUNCH1
 #undef EFFDET_TCM_LAUNCH
     return launch_status("conv_tc_multi_kernel");
 }
