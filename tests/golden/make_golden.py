@@ -76,9 +76,11 @@ def must_equal(name, a, b):
         raise SystemExit('oracle != reference at %s (max abs %g)' % (name, float((a - b).abs().max())))
 
 
-def run_forward_case(tag, cfg, mode, size, B, seed):
+def run_forward_case(tag, cfg, mode, size, B, seed, threshold=None):
     sd = O.init_state_dict(cfg, seed=seed, mode=mode)
-    ref = build_reference(cfg, sd, is_training=False, threshold=0.3 if mode == 'wellcond' else 0.01)
+    if threshold is None:
+        threshold = 0.3 if mode == 'wellcond' else 0.01
+    ref = build_reference(cfg, sd, is_training=False, threshold=threshold)
     ref.eval()
     images, _ = O.synthetic_batch(B, size=size, seed=100 + seed)
     cap = {}
@@ -206,13 +208,27 @@ def run_nms_case():
 
 
 if __name__ == '__main__':
+    # usage: make_golden.py [substring]   -- regenerate only the fixtures whose tag contains the substring
+    only = sys.argv[1] if len(sys.argv) > 1 else ''
     torch.set_num_threads(8)
     d0 = O.make_config('efficientdet-d0', num_classes=80, W_bifpn=64, D_bifpn=2)
-    run_nms_case()
-    run_forward_case('d0_512_fwd_wellcond', d0, 'wellcond', 512, 1, seed=1)
-    run_forward_case('d0_512_fwd_asbuilt', d0, 'asbuilt', 512, 1, seed=2)
     d0s = O.make_config('efficientdet-d0', num_classes=20, W_bifpn=64, D_bifpn=2)
-    run_train_case('d0_256_train_b2', d0s, 256, 2, seed=3, empty_first=False)
-    run_train_case('d0_256_train_b2_empty', d0s, 256, 2, seed=4, empty_first=True)
     d1 = O.make_config('efficientdet-d1', num_classes=20, W_bifpn=88, D_bifpn=3)
-    run_forward_case('d1_384_fwd_wellcond', d1, 'wellcond', 384, 1, seed=5)
+    # the deep / wide family members whose GPU tests (D4 1024^2 train step, D7 1536^2 inference) compare against the
+    # ORACLE: pin the oracle to the reference on the same architectures at a CPU-sized resolution
+    d4 = O.make_config('efficientdet-d4', num_classes=20, W_bifpn=224, D_bifpn=6)
+    d7 = O.make_config('efficientdet-d7', num_classes=20, W_bifpn=384, D_bifpn=8)
+    cases = [
+        ('nms_torchvision', run_nms_case, ()),
+        ('d0_512_fwd_wellcond', run_forward_case, (d0, 'wellcond', 512, 1, 1)),
+        ('d0_512_fwd_asbuilt', run_forward_case, (d0, 'asbuilt', 512, 1, 2)),
+        ('d0_256_train_b2', run_train_case, (d0s, 256, 2, 3, False)),
+        ('d0_256_train_b2_empty', run_train_case, (d0s, 256, 2, 4, True)),
+        ('d1_384_fwd_wellcond', run_forward_case, (d1, 'wellcond', 384, 1, 5)),
+        ('d4_256_fwd_wellcond', run_forward_case, (d4, 'wellcond', 256, 1, 6, 0.05)),
+        ('d4_128_train_b2', run_train_case, (d4, 128, 2, 7, False)),
+        ('d7_256_fwd_wellcond', run_forward_case, (d7, 'wellcond', 256, 1, 8, 0.05)),
+    ]
+    for tag, fn, a in cases:
+        if only in tag:
+            fn(*((tag,) + a)) if fn is not run_nms_case else fn()

@@ -25,6 +25,9 @@ def _check(store, name, t):
     ('d0_512_fwd_wellcond', 'efficientdet-d0', 64, 2, 80, 'wellcond'),
     ('d0_512_fwd_asbuilt', 'efficientdet-d0', 64, 2, 80, 'asbuilt'),
     ('d1_384_fwd_wellcond', 'efficientdet-d1', 88, 3, 20, 'wellcond'),
+    # the architectures whose GPU tests (D4 1024^2 train step, D7 1536^2 inference) use the oracle as the checker
+    ('d4_256_fwd_wellcond', 'efficientdet-d4', 224, 6, 20, 'wellcond'),
+    ('d7_256_fwd_wellcond', 'efficientdet-d7', 384, 8, 20, 'wellcond'),
 ])
 def test_forward_matches_reference_golden(tag, net, W, D, K, mode):
     st = np.load(os.path.join(G, tag + '.npz'))
@@ -52,11 +55,13 @@ def test_forward_matches_reference_golden(tag, net, W, D, K, mode):
     assert np.array_equal(det[2].numpy(), st['det/boxes'])
 
 
-@pytest.mark.parametrize('tag', ['d0_256_train_b2', 'd0_256_train_b2_empty'])
-def test_train_step_matches_reference_golden(tag):
+@pytest.mark.parametrize('tag,net,W,D,nlive', [('d0_256_train_b2', 'efficientdet-d0', 64, 2, 274),
+                                               ('d0_256_train_b2_empty', 'efficientdet-d0', 64, 2, 274),
+                                               ('d4_128_train_b2', 'efficientdet-d4', 224, 6, 551)])
+def test_train_step_matches_reference_golden(tag, net, W, D, nlive):
     st = np.load(os.path.join(G, tag + '.npz'))
     seed, size, B, empty = [int(v) for v in st['meta/seed']]
-    cfg = O.make_config('efficientdet-d0', num_classes=20, W_bifpn=64, D_bifpn=2)
+    cfg = O.make_config(net, num_classes=20, W_bifpn=W, D_bifpn=D)
     sd = O.init_state_dict(cfg, seed=seed, mode='wellcond')
     images, ann = O.synthetic_batch(B, size=size, num_classes=20, seed=200 + seed, empty_first=bool(empty))
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v)
@@ -66,7 +71,7 @@ def test_train_step_matches_reference_golden(tag):
     assert np.array_equal(cl.detach().numpy(), st['loss/cls'])
     assert np.array_equal(rl.detach().numpy(), st['loss/reg'])
     names, norms = list(st['grad_names']), st['grad_norms']
-    assert len(names) == 274
+    assert len(names) == nlive
     for k, n in zip(names, norms):
         g = sdg[str(k)].grad
         gn = float(torch.linalg.vector_norm(g.double()))
