@@ -71,6 +71,10 @@ __global__ void __launch_bounds__(kNT, 2) conv_igemm_kernel(const effdet_conv_ar
             float4 v = f4zero();
             if (ok) {
                 v = ldg4(p.x + a_off[j] + ((long long)iy * p.W + ix) * p.Cin + c);
+                if (p.in_scale) {                      // raw conv output -> swish(bn(.)) while the tile is staged
+                    const float4 u = f4fma(v, ldg4(p.in_scale + c), ldg4(p.in_shift + c));
+                    v = make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w));
+                }
                 if (p.a_scale) v = f4mul(v, ldg4(p.a_scale + (long long)a_b[j] * p.Cin + c));
             }
             ra[j] = v;
@@ -223,6 +227,10 @@ __global__ void __launch_bounds__(kNT, 2) conv_wgrad_kernel(const effdet_wgrad_a
                     const int iy = oy + ky - pad, ix = ox + kx - pad;
                     if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
                         v = ldg4(p.x + (long long)b * p.x_bstride + ((long long)iy * p.W + ix) * p.Cin + c);
+                        if (p.in_scale) {
+                            const float4 u = f4fma(v, ldg4(p.in_scale + c), ldg4(p.in_shift + c));
+                            v = make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w));
+                        }
                         if (p.a_scale) v = f4mul(v, ldg4(p.a_scale + (long long)b * p.Cin + c));
                     }
                 }
@@ -365,6 +373,9 @@ extern "C" int effdet_conv2d(const effdet_conv_args* a, int device, effdet_strea
     EFFDET_REQUIRE(a->Cin % 4 == 0 && a->Cout % 4 == 0, "conv2d: Cin=%d Cout=%d must be multiples of 4", a->Cin, a->Cout);
     EFFDET_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv2d: empty shape");
     EFFDET_REQUIRE((a->scale == nullptr) == (a->shift == nullptr), "conv2d: scale/shift must come together");
+    EFFDET_REQUIRE((a->in_scale == nullptr) == (a->in_shift == nullptr) && (!a->in_scale || a->ksize == 1),
+                   "conv2d: in_scale/in_shift must come together (1x1 convs only: zero padding is applied after the activation)");
+    EFFDET_REQUIRE(aligned16(a->in_scale) && aligned16(a->in_shift), "conv2d: in_scale/in_shift must be 16-byte aligned");
     EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->w) && aligned16(a->y) && aligned16(a->z) && aligned16(a->bias) &&
                        aligned16(a->residual) && aligned16(a->mask_src) && aligned16(a->a_scale),
                    "conv2d: pointers must be 16-byte aligned");
@@ -418,7 +429,10 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     EFFDET_REQUIRE(a && a->x && a->dy && a->dw, "wgrad: null tensor");
     EFFDET_REQUIRE(a->ksize == 1 || a->ksize == 3, "wgrad: ksize %d not in {1,3}", a->ksize);
     EFFDET_REQUIRE(a->Cin % 4 == 0 && a->Cout % 4 == 0, "wgrad: channels must be multiples of 4");
-    EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->dy) && aligned16(a->a_scale), "wgrad: pointers must be 16-byte aligned");
+    EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->dy) && aligned16(a->a_scale) && aligned16(a->in_scale) && aligned16(a->in_shift),
+                   "wgrad: pointers must be 16-byte aligned");
+    EFFDET_REQUIRE((a->in_scale == nullptr) == (a->in_shift == nullptr) && (!a->in_scale || a->ksize == 1),
+                   "wgrad: in_scale/in_shift must come together (1x1 convs only)");
     EFFDET_REQUIRE(a->x_bstride % 4 == 0 && a->dy_bstride % 4 == 0, "wgrad: batch strides must be multiples of 4");
     EFFDET_DEVICE(device);
     const long long Mll = (long long)a->B * a->H * a->W;

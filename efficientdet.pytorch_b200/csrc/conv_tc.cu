@@ -256,19 +256,43 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
                         const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
                         v[2 * i] = ldg4(src);
                         if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
-                        if (MB && p.a_scale) {                 // squeeze-excite gate on the input (per image, channel)
-                            const float* gp = p.a_scale + (base[i] / p.x_bstride) * p.Cin + c;
-                            v[2 * i] = f4mul(v[2 * i], ldg4(gp));
-                            if (c + 4 < p.Cin) v[2 * i + 1] = f4mul(v[2 * i + 1], ldg4(gp + 4));
-                        }
                     }
                 }
             }
         };
+        // input prologue of the MBConv project conv (applied when the stage is converted, so the loads of the next
+        // stage stay in flight): eval-BN + swish of the raw depthwise output, then the squeeze-excite gate.
+        // Zero-filled elements (rows beyond M, channels beyond Cin) must stay zero, hence the validity tests.
+        auto prologue = [&](int kt, float4 (&v)[8]) {
+            const int tap = kt / kblocks;
+            const int c = (kt - tap * kblocks) * kTileK + j * 8;
+            if (c >= p.Cin) return;
+            const bool hi_ok = c + 4 < p.Cin;
+            float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0, h0 = f4zero(), h1 = f4zero();
+            if (p.in_scale) {
+                s0 = ldg4(p.in_scale + c); h0 = ldg4(p.in_shift + c);
+                if (hi_ok) { s1 = ldg4(p.in_scale + c + 4); h1 = ldg4(p.in_shift + c + 4); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (oyx[i] < 0) continue;
+                if (p.in_scale) {
+                    const float4 u0 = f4fma(v[2 * i], s0, h0), u1 = f4fma(v[2 * i + 1], s1, h1);
+                    v[2 * i] = make_float4(swishf_(u0.x), swishf_(u0.y), swishf_(u0.z), swishf_(u0.w));
+                    v[2 * i + 1] = hi_ok ? make_float4(swishf_(u1.x), swishf_(u1.y), swishf_(u1.z), swishf_(u1.w)) : f4zero();
+                }
+                if (p.a_scale) {                               // squeeze-excite gate on the input (per image, channel)
+                    const float* gp = p.a_scale + (base[i] / p.x_bstride) * p.Cin + c;
+                    v[2 * i] = f4mul(v[2 * i], ldg4(gp));
+                    if (hi_ok) v[2 * i + 1] = f4mul(v[2 * i + 1], ldg4(gp + 4));
+                }
+            }
+        };
         // split to bf16 hi/lo and publish the stage to the MMA warp
-        auto store_stage = [&](int kt, const float4 (&v)[8]) {
+        auto store_stage = [&](int kt, float4 (&v)[8]) {
             const int s = kt % STAGES;
             const uint32_t ph = (kt / STAGES) & 1;
+            if (MB && (p.in_scale || p.a_scale)) prologue(kt, v);
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* a_hi = smem + s * S::kStage;
             uint8_t* a_lo = a_hi + S::kA;
@@ -1405,7 +1429,9 @@ wgrad_tc2_pair_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_co
 
 // fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ a_scale,
-                                                           __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad) {
+                                                           __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad,
+                                                           const float* __restrict__ in_scale = nullptr,
+                                                           const float* __restrict__ in_shift = nullptr) {
     const int cv = Cpad / 8;
     const long long total = (long long)B * HW * cv;
     const long long plane = (long long)B * HW * Cpad;
@@ -1420,6 +1446,14 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             const float* q = x + (long long)b * bstride + pix * C + c;
             v0 = ldg4(q);
             if (c + 4 < C) v1 = ldg4(q + 4);
+            if (in_scale) {                        // operand = swish(bn(x)) of a raw conv output (pre-activation only in HBM)
+                const float4 u0 = f4fma(v0, ldg4(in_scale + c), ldg4(in_shift + c));
+                v0 = make_float4(swishf_(u0.x), swishf_(u0.y), swishf_(u0.z), swishf_(u0.w));
+                if (c + 4 < C) {
+                    const float4 u1 = f4fma(v1, ldg4(in_scale + c + 4), ldg4(in_shift + c + 4));
+                    v1 = make_float4(swishf_(u1.x), swishf_(u1.y), swishf_(u1.z), swishf_(u1.w));
+                }
+            }
             if (a_scale) {
                 v0 = f4mul(v0, ldg4(a_scale + (long long)b * C + c));
                 if (c + 4 < C) v1 = f4mul(v1, ldg4(a_scale + (long long)b * C + c + 4));
@@ -1573,7 +1607,7 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
     dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
-    const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
+    const bool mb = a->a_scale || a->z || a->scale || a->row_scale || a->in_scale;
     const bool coal = coalesced_epilogue_enabled();
 #define EFFDET_TC_LAUNCH1(BN_, ST_, MB_, CO_)                                                                              \
     do {                                                                                                                  \
@@ -1686,7 +1720,7 @@ bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
     if (a->precision != 1 || a->Cin % 4 || a->Cout % 4 || a->Cin < 16 || a->Cout < 16) return false;
     WgGeom g;
     const bool tma_ok = a->ws_x && a->ws_dy && wg_geometry(a->B, a->H, a->W, &g);
-    return tma_ok || !a->a_scale;     // the gather-producer fallback has no input gate
+    return tma_ok || (!a->a_scale && !a->in_scale);     // the gather-producer fallback has no input prologue
 }
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g) {
@@ -1727,7 +1761,8 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     const int cin_pad = conv_tc_kpad(a->Cin), cout_pad = conv_tc_kpad(a->Cout);
     int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
+    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad,
+                                                a->in_scale, a->in_shift);
     int s = launch_status("split_planes_kernel");
     if (s) return s;
     if ((s = split_dy_launch(a, cout_pad, st))) return s;      // also accumulates the bias gradient
@@ -1772,7 +1807,7 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     int chunks = 0;
     for (int l = 0; l < nlevels; ++l) {
         const effdet_wgrad_args* a = &levels[l];
-        if (!a->ws_x || !a->ws_dy || a->a_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
+        if (!a->ws_x || !a->ws_dy || a->a_scale || a->in_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
         ma.chunk_begin[l] = chunks;
         chunks += ma.g[l].nbx * ma.g[l].nby * ma.g[l].nbb;
     }
@@ -1908,7 +1943,7 @@ extern "C" int effdet_conv2d_multi(const effdet_conv_args* levels, int nlevels, 
                            a->act == levels[0].act && a->w == levels[0].w && a->w_tc == levels[0].w_tc &&
                            a->bias == levels[0].bias,
                        "conv2d_multi: all levels must share weights, bias, channels and activation");
-        const bool mb = a->a_scale || a->z || a->scale || a->row_scale;
+        const bool mb = a->a_scale || a->z || a->scale || a->row_scale || a->in_scale;
         tc = tc && conv_tc_eligible(a) && !mb && (long long)a->B * a->H * a->W < (1ll << 31);
         EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->y) && aligned16(a->residual) && aligned16(a->mask_src) &&
                            a->x_bstride % 4 == 0 && a->y_bstride % 4 == 0 && a->r_bstride % 4 == 0 && a->m_bstride % 4 == 0,

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const float* __restrict__
     }
     const long long o = (((long long)b * Ho + oy) * Wo + ox) * C0 + cv * 4;
     st4(z + o, acc);
+    if (y == nullptr) return;
     float4 u = f4fma(acc, ldg4(scale + cv * 4), ldg4(shift + cv * 4));
     st4(y + o, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
 }
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(128) stem_fwd_px_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         st4(zo + j * 4, acc[j]);
+        if (y == nullptr) continue;
         const float4 u = f4fma(acc[j], *reinterpret_cast<const float4*>(&sc_s[j * 4]), *reinterpret_cast<const float4*>(&sh_s[j * 4]));
         st4(yo + j * 4, make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w)));
     }
@@ -172,7 +174,7 @@ using namespace effdet;
 
 extern "C" int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift,
                                float* z, float* y, int B, int H, int W, int C0, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(x_nchw && w_oihw && scale && shift && z && y, "stem_fwd: null tensor");
+    EFFDET_REQUIRE(x_nchw && w_oihw && scale && shift && z, "stem_fwd: null tensor");
     EFFDET_REQUIRE(C0 % 4 == 0 && C0 > 0 && C0 <= 256, "stem_fwd: C0=%d unsupported", C0);
     EFFDET_REQUIRE(B > 0 && H >= 2 && W >= 2, "stem_fwd: bad shape");
     EFFDET_REQUIRE(aligned16(z) && aligned16(y) && aligned16(scale) && aligned16(shift), "stem_fwd: alignment");

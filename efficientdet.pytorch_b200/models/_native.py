@@ -14,8 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'stem.cu', 'depthwise.cu', 'mbconv_ops.cu', 'bifpn.cu', 'loss.cu',
-           'detect.cu', 'layout.cu', 'optim.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu',
+           'loss.cu', 'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -28,19 +28,40 @@ class EffdetNativeError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile the sm_100a shared object in-tree with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, 'common.cuh'),
-                   os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'effdet_b200.h'))]
-    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
-        return SO_PATH
+    """Compile the sm_100a shared object in-tree with nvcc (cross-compiles without a GPU): one object per .cu,
+    compiled in parallel and only when stale, then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
+    import hashlib
+    hdrs = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc_ptx.cuh'),
+            os.path.normpath(os.path.join(CSRC, '..', '..', 'include', 'effdet_b200.h'))]
+    hdr_blob = b''.join(open(h, 'rb').read() for h in hdrs if os.path.exists(h))
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', SO_PATH] + srcs
-    if verbose:
-        print(' '.join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise EffdetNativeError('nvcc failed:\n' + r.stdout + r.stderr)
+    flags = [f for f in NVCC_FLAGS if f != '-shared']
+    jobs, stamps = [], []
+    for s in SOURCES:                      # staleness by CONTENT (file times do not survive the trip to the GPU box)
+        src, obj = os.path.join(CSRC, s), os.path.join(CSRC, s[:-3] + '.o')
+        digest = hashlib.sha1(open(src, 'rb').read() + hdr_blob + ' '.join(flags).encode()).hexdigest()
+        stamp = obj + '.sha1'
+        have = open(stamp).read().strip() if os.path.exists(stamp) else ''
+        if force or not os.path.exists(obj) or have != digest:
+            jobs.append([nvcc] + flags + ['-c', src, '-o', obj])
+            stamps.append((stamp, digest))
+
+    def run(cmd):
+        if verbose:
+            print(' '.join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise EffdetNativeError('nvcc failed:\n' + r.stdout + r.stderr)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(run, jobs))
+        for stamp, digest in stamps:
+            open(stamp, 'w').write(digest)
+    objs = [os.path.join(CSRC, s[:-3] + '.o') for s in SOURCES]
+    if jobs or not os.path.exists(SO_PATH):
+        run([nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', SO_PATH] + objs)
     return SO_PATH
 
 
@@ -55,19 +76,33 @@ class ConvArgs(ctypes.Structure):
                 ('bias', _P), ('scale', _P), ('shift', _P), ('a_scale', _P), ('row_scale', _P),
                 ('residual', _P), ('r_bstride', _I64), ('mask_src', _P), ('m_bstride', _I64),
                 ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32),
-                ('w_tc', _P)]
+                ('w_tc', _P), ('in_scale', _P), ('in_shift', _P)]
 
 
 class WgradArgs(ctypes.Structure):
     _fields_ = [('x', _P), ('x_bstride', _I64), ('dy', _P), ('dy_bstride', _I64), ('dw', _P), ('dbias', _P),
                 ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32),
-                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P)]
+                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P), ('in_scale', _P), ('in_shift', _P)]
 
 
 class BnActBwdArgs(ctypes.Structure):
     _fields_ = [('dy', _P), ('z', _P), ('dz', _P), ('scale', _P), ('shift', _P), ('mean', _P), ('rstd', _P),
                 ('dgamma', _P), ('dbeta', _P), ('row_scale', _P), ('gate', _P), ('dmean', _P), ('inv_hw', _F),
                 ('B', _I32), ('HW', _I32), ('C', _I32), ('act', _I32)]
+
+
+class DwFwdArgs(ctypes.Structure):
+    _fields_ = [('x', _P), ('in_scale', _P), ('in_shift', _P), ('w_kkc', _P), ('scale', _P), ('shift', _P), ('z', _P),
+                ('se_sum', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('k', _I32), ('stride', _I32),
+                ('pad_t', _I32), ('pad_l', _I32), ('Ho', _I32), ('Wo', _I32), ('se_alpha', _F)]
+
+
+class DwBwdArgs(ctypes.Structure):
+    _fields_ = [('dq', _P), ('z1', _P), ('gate', _P), ('dmean', _P), ('scale1', _P), ('shift1', _P), ('mean1', _P),
+                ('rstd1', _P), ('x', _P), ('scale0', _P), ('shift0', _P), ('mean0', _P), ('rstd0', _P), ('w_kkc', _P),
+                ('dx', _P), ('dw', _P), ('dgamma1', _P), ('dbeta1', _P), ('dgamma0', _P), ('dbeta0', _P),
+                ('inv_hw', _F), ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('k', _I32), ('stride', _I32),
+                ('pad_t', _I32), ('pad_l', _I32), ('Ho', _I32), ('Wo', _I32)]
 
 
 class FuseArgs(ctypes.Structure):
@@ -99,11 +134,14 @@ SIGNATURES = {
     'effdet_dwconv_bwd_data': [_P, _P, _P] + [_INT] * 10 + _TAIL,
     'effdet_dwconv_bwd_weight': [_P, _P, _P] + [_INT] * 10 + _TAIL,
     'effdet_pack_dw_weight': [_P, _P, _INT, _INT] + _TAIL,
+    'effdet_dwconv_fwd_fused': [ctypes.POINTER(DwFwdArgs)] + _TAIL,
+    'effdet_dwconv_bwd_fused': [ctypes.POINTER(DwBwdArgs)] + _TAIL,
     'effdet_bnact_bwd': [ctypes.POINTER(BnActBwdArgs)] + _TAIL,
     'effdet_bn_fold': [_P, _P, _P, _P, _F, _P, _P, _P, _INT] + _TAIL,
     'effdet_add': [_P, _P, _P, _I64] + _TAIL,
     'effdet_relu_bwd': [_P, _P, _P, _I64] + _TAIL,
     'effdet_spatial_reduce': [_P, _P, _P, _F, _INT, _INT, _INT] + _TAIL,
+    'effdet_spatial_reduce_act': [_P, _P, _P, _P, _P, _F, _INT, _INT, _INT] + _TAIL,
     'effdet_se_gate_fwd': [_P] * 7 + [_INT] * 3 + _TAIL,
     'effdet_se_gate_bwd': [_P] * 11 + [_INT] * 3 + _TAIL,
     'effdet_bifpn_fuse_fwd': [ctypes.POINTER(FuseArgs)] + _TAIL,

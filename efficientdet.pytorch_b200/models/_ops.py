@@ -180,24 +180,27 @@ def bn_fold(gamma, beta, rmean, rvar, eps):
 
 def conv2d_raw(dev_t, x_ptr, x_bs, wf, y_ptr, y_bs, B, H, W, Cin, Cout, k, z_ptr=None, bias=None, scale=None,
                shift=None, a_scale=None, row_scale=None, res_ptr=None, res_bs=0, mask_ptr=None, mask_bs=0,
-               act=ACT_NONE, w_tc=None):
+               act=ACT_NONE, w_tc=None, in_scale=None, in_shift=None):
     a = N.ConvArgs(x_ptr, x_bs, N.f32(wf, 'packed weight'), y_ptr, y_bs, z_ptr, N.f32(bias, 'bias'),
                    N.f32(scale, 'scale'), N.f32(shift, 'shift'), N.f32(a_scale, 'a_scale'),
                    N.f32(row_scale, 'row_scale'), res_ptr, res_bs, mask_ptr, mask_bs, B, H, W, Cin, Cout, k, act,
-                   w_tc.data_ptr() if w_tc is not None else None)
+                   w_tc.data_ptr() if w_tc is not None else None, N.f32(in_scale, 'in_scale'),
+                   N.f32(in_shift, 'in_shift'))
     N.call('effdet_conv2d', dev_t, a)
 
 
 def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_scale=None, residual=None,
-           mask_src=None, act=ACT_NONE, save_z=False, w_tc=None):
-    """x NHWC contiguous -> y NHWC (and the raw pre-affine z when save_z)."""
+           mask_src=None, act=ACT_NONE, save_z=False, w_tc=None, in_scale=None, in_shift=None):
+    """x NHWC contiguous -> y NHWC (and the raw pre-affine z when save_z).  in_scale/in_shift: x is a raw conv
+    output and the operand is swish(x*in_scale+in_shift), applied while the tile is staged."""
     B, H, W, Cin = x.shape
     y = _empty((B, H, W, Cout), x)
     z = _empty((B, H, W, Cout), x) if save_z else None
     bs = H * W * Cout
     conv2d_raw(x, N.f32(x, 'x'), H * W * Cin, wf, N.f32(y), bs, B, H, W, Cin, Cout, k, z_ptr=N.f32(z), bias=bias,
                scale=scale, shift=shift, a_scale=a_scale, row_scale=row_scale, res_ptr=N.f32(residual, 'residual'),
-               res_bs=bs, mask_ptr=N.f32(mask_src, 'mask_src'), mask_bs=bs, act=act, w_tc=w_tc)
+               res_bs=bs, mask_ptr=N.f32(mask_src, 'mask_src'), mask_bs=bs, act=act, w_tc=w_tc, in_scale=in_scale,
+               in_shift=in_shift)
     return (y, z) if save_z else y
 
 
@@ -232,7 +235,8 @@ def conv2d_multi(xs, wf, Cout, k, bias=None, act=ACT_NONE, w_tc=None, residuals=
     return ys
 
 
-def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False):
+def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False,
+                   in_scale=None, in_shift=None):
     ws_x = ws_dy = None
     if tc:
         lib = N.load()
@@ -240,7 +244,8 @@ def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, C
         ws_dy = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cout),), device=dev_t.device, dtype=torch.bfloat16)
     a = N.WgradArgs(x_ptr, x_bs, dy_ptr, dy_bs, N.f32(dw, 'dw'), N.f32(dbias, 'dbias'), N.f32(a_scale, 'a_scale'),
                     B, H, W, Cin, Cout, k, 1 if tc else 0, ws_x.data_ptr() if ws_x is not None else None,
-                    ws_dy.data_ptr() if ws_dy is not None else None)
+                    ws_dy.data_ptr() if ws_dy is not None else None, N.f32(in_scale, 'in_scale'),
+                    N.f32(in_shift, 'in_shift'))
     N.call('effdet_conv2d_wgrad', dev_t, a)
 
 
@@ -265,11 +270,11 @@ def conv_wgrad_multi(dev_t, levels, dw, dbias, Cin, Cout, k, tc=False):
     N.call('effdet_conv2d_wgrad_multi', dev_t, arr, nl)
 
 
-def conv_wgrad(x, dy, dw, dbias, k, a_scale=None, tc=False):
+def conv_wgrad(x, dy, dw, dbias, k, a_scale=None, tc=False, in_scale=None, in_shift=None):
     B, H, W, Cin = x.shape
     Cout = dy.shape[3]
     conv_wgrad_raw(x, N.f32(x, 'x'), H * W * Cin, N.f32(dy, 'dy'), H * W * Cout, dw, dbias, B, H, W, Cin, Cout, k,
-                   a_scale=a_scale, tc=tc)
+                   a_scale=a_scale, tc=tc, in_scale=in_scale, in_shift=in_shift)
 
 
 def bnact_bwd(dy, z, scale, shift, mean, rstd, act, row_scale=None, gate=None, dmean=None):
@@ -341,7 +346,12 @@ class StemFn(torch.autograd.Function):
 
 class MBConvFn(torch.autograd.Function):
     """args: x (NHWC), row_scale ([B] drop-connect multiplier or None), cfg dict, then parameters
-    [We,g0,b0,rm0,rv0]? Wd,g1,b1,rm1,rv1, Wr,br,Wx,bx, Wp,g2,b2,rm2,rv2."""
+    [We,g0,b0,rm0,rv0]? Wd,g1,b1,rm1,rv1, Wr,br,Wx,bx, Wp,g2,b2,rm2,rv2.
+
+    Only PRE-activations live in HBM, like the reference's MemoryEfficientSwish (models/utils.py:31-42): the expand
+    GEMM writes the raw z0, the depthwise kernel applies BN0+swish while staging z0 and writes the raw z1 (its epilogue
+    also yields the squeeze-excite mean), the project GEMM applies BN1+swish+gate while staging z1.  Forward = 4
+    launches; backward never materialises dz1 / da0 (effdet_dwconv_bwd_fused)."""
 
     @staticmethod
     def forward(ctx, x, row_scale, cfg, *P):
@@ -355,11 +365,11 @@ class MBConvFn(torch.autograd.Function):
             i = 5
             sc0, sh0, rs0 = bn_fold(g0, b0, rm0, rv0, eps)
             wf, _ = pack_conv(We)
-            a0, z0 = conv2d(x, wf, We.shape[0], 1, scale=sc0, shift=sh0, act=ACT_SWISH, save_z=True,
-                            w_tc=tc_packs(We)[0])
+            z0 = conv2d(x, wf, We.shape[0], 1, w_tc=tc_packs(We)[0])          # raw: BN0 + swish happen in the consumer
             saved.update(z0=z0, sc0=sc0, sh0=sh0, rs0=rs0, rm0=rm0)
+            dw_in, isc, ish = z0, sc0, sh0
         else:
-            a0 = x
+            dw_in, isc, ish = x, None, None
         Wd, g1, b1, rm1, rv1, Wr, br, Wx, bx, Wp, g2, b2, rm2, rv2 = P[i:i + 14]
         C = Wd.shape[0]
         sc1, sh1, rs1 = bn_fold(g1, b1, rm1, rv1, eps)
@@ -367,31 +377,29 @@ class MBConvFn(torch.autograd.Function):
         Ho = (H + cfg['pad_h'] - k) // s + 1
         Wo = (W + cfg['pad_w'] - k) // s + 1
         z1 = _empty((B, Ho, Wo, C), x)
-        a1 = _empty((B, Ho, Wo, C), x)
-        wkkc = pack_dw(Wd)
-        N.call('effdet_dwconv_fwd', x, N.f32(a0), N.f32(wkkc), N.f32(sc1), N.f32(sh1), N.f32(z1), N.f32(a1),
-               B, H, W, C, k, s, pt, pl, Ho, Wo, nbytes=4.0 * (a0.numel() + 2 * z1.numel()))
-        # squeeze-excite
-        S = Wr.shape[0]
         mean = _zeros((B, C), x)
-        N.call('effdet_spatial_reduce', x, N.f32(a1), None, N.f32(mean), 1.0 / (Ho * Wo), B, Ho * Wo, C,
-               nbytes=4.0 * a1.numel())
+        wkkc = pack_dw(Wd)
+        fa = N.DwFwdArgs(N.f32(dw_in), N.f32(isc), N.f32(ish), N.f32(wkkc), N.f32(sc1), N.f32(sh1), N.f32(z1),
+                         N.f32(mean), B, H, W, C, k, s, pt, pl, Ho, Wo, 1.0 / (Ho * Wo))
+        N.call('effdet_dwconv_fwd_fused', x, fa, nbytes=4.0 * (dw_in.numel() + z1.numel()))
+        # squeeze-excite gate from the mean the depthwise epilogue accumulated
+        S = Wr.shape[0]
         s_pre = _empty((B, S), x)
         gate = _empty((B, C), x)
         wr, wx = _contig(Wr.detach()), _contig(Wx.detach())
         N.call('effdet_se_gate_fwd', x, N.f32(mean), N.f32(wr), N.f32(br.detach()), N.f32(wx), N.f32(bx.detach()),
                N.f32(s_pre), N.f32(gate), B, C, S)
-        # project (+BN, drop-connect, skip)
+        # project: operand swish(bn1(z1)) * gate built while staging, then BN2, drop-connect, skip
         sc2, sh2, rs2 = bn_fold(g2, b2, rm2, rv2, eps)
         wpf, _ = pack_conv(Wp)
         Cout = Wp.shape[0]
         skip = cfg['skip']
-        y, z2 = conv2d(a1, wpf, Cout, 1, scale=sc2, shift=sh2, a_scale=gate,
+        y, z2 = conv2d(z1, wpf, Cout, 1, scale=sc2, shift=sh2, a_scale=gate, in_scale=sc1, in_shift=sh1,
                        row_scale=row_scale if skip else None, residual=x if skip else None, save_z=True,
                        w_tc=tc_packs(Wp)[0])
         ctx.cfg = cfg
         ctx.P = P
-        ctx.t = dict(saved, x=x, a0=a0, z1=z1, a1=a1, mean=mean, s_pre=s_pre, gate=gate, z2=z2, sc1=sc1, sh1=sh1,
+        ctx.t = dict(saved, x=x, z1=z1, mean=mean, s_pre=s_pre, gate=gate, z2=z2, sc1=sc1, sh1=sh1,
                      rs1=rs1, rm1=rm1, sc2=sc2, sh2=sh2, rs2=rs2, rm2=rm2, row_scale=row_scale if skip else None,
                      wkkc=wkkc, dims=(B, H, W, Ho, Wo))
         return y
@@ -399,53 +407,59 @@ class MBConvFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         cfg, P, t = ctx.cfg, ctx.P, ctx.t
+        if t is None:
+            raise RuntimeError('MBConvFn: backward called twice (activations are released after the first backward)')
         dy = _contig(dy)
         x = t['x']
         B, H, W, Ho, Wo = t['dims']
         k, s = cfg['k'], cfg['s']
-        i = 5 if cfg['expand'] else 0
+        expand = cfg['expand']
+        i = 5 if expand else 0
         Wd, g1, b1, rm1, rv1, Wr, br, Wx, bx, Wp, g2, b2, rm2, rv2 = P[i:i + 14]
         C = Wd.shape[0]
-        a1, gate = t['a1'], t['gate']
+        z1, gate = t['z1'], t['gate']
         # project BN (no activation), drop-connect scale folded in
         dz2, dg2, db2 = bnact_bwd(dy, t['z2'], t['sc2'], t['sh2'], t['rm2'], t['rs2'], ACT_NONE,
                                   row_scale=t['row_scale'])
-        zb = _zeros_like_many([Wp, Wr, br, Wx, bx, Wd] + ([P[0]] if cfg['expand'] else []))
+        zb = _zeros_like_many([Wp, Wr, br, Wx, bx, Wd, g1, b1] + ([P[0], P[1], P[2]] if expand else []))
         dWp = zb[0]
-        conv_wgrad(a1, dz2, dWp, None, 1, a_scale=gate, tc=tc_enabled())
+        conv_wgrad(z1, dz2, dWp, None, 1, a_scale=gate, tc=tc_enabled(), in_scale=t['sc1'], in_shift=t['sh1'])
         _, wpd = pack_conv(Wp)
         dq = conv2d(dz2, wpd, C, 1, w_tc=tc_packs(Wp)[1])     # grad w.r.t. (a1 * gate)
-        # squeeze-excite backward
+        # squeeze-excite backward: dgate = sum_px dq * swish(bn1(z1)) with the activation recomputed
         dgate = _zeros((B, C), x)
-        N.call('effdet_spatial_reduce', x, N.f32(dq), N.f32(a1), N.f32(dgate), 1.0, B, Ho * Wo, C,
-               nbytes=8.0 * a1.numel())
+        N.call('effdet_spatial_reduce_act', x, N.f32(dq), N.f32(z1), N.f32(t['sc1']), N.f32(t['sh1']), N.f32(dgate), 1.0,
+               B, Ho * Wo, C, nbytes=8.0 * z1.numel())
         S = Wr.shape[0]
         dmean = _empty((B, C), x)
         dWr, dbr, dWx, dbx = zb[1], zb[2], zb[3], zb[4]
         N.call('effdet_se_gate_bwd', x, N.f32(dgate), N.f32(t['mean']), N.f32(t['s_pre']), N.f32(gate),
                N.f32(_contig(Wr.detach())), N.f32(_contig(Wx.detach())), N.f32(dmean), N.f32(dWr), N.f32(dbr),
                N.f32(dWx), N.f32(dbx), B, C, S)
-        # depthwise BN+swish backward with the SE product rule fused in
-        dz1, dg1, db1 = bnact_bwd(dq, t['z1'], t['sc1'], t['sh1'], t['rm1'], t['rs1'], ACT_SWISH, gate=gate,
-                                  dmean=dmean)
-        a0 = t['a0']
-        dWd = zb[5]
-        N.call('effdet_dwconv_bwd_weight', x, N.f32(a0), N.f32(dz1), N.f32(dWd), B, H, W, C, k, s, cfg['pad_t'],
-               cfg['pad_l'], Ho, Wo, nbytes=4.0 * (a0.numel() + dz1.numel()))
-        da0 = _empty((B, H, W, C), x)
-        N.call('effdet_dwconv_bwd_data', x, N.f32(dz1), N.f32(t['wkkc']), N.f32(da0), B, H, W, C, k, s,
-               cfg['pad_t'], cfg['pad_l'], Ho, Wo, nbytes=4.0 * (dz1.numel() + da0.numel()))
+        # BN1+swish backward (SE product rule), depthwise weight + data gradient, BN0+swish backward: one pass
+        dWd, dg1, db1 = zb[5], zb[6], zb[7]
+        dw_in = t['z0'] if expand else x
+        dxe = _empty((B, H, W, C), x)
+        dg0 = db0 = None
+        if expand:
+            dg0, db0 = zb[9], zb[10]
+        ba = N.DwBwdArgs(N.f32(dq), N.f32(z1), N.f32(gate), N.f32(dmean), N.f32(t['sc1']), N.f32(t['sh1']),
+                         N.f32(t['rm1'], 'mean'), N.f32(t['rs1']), N.f32(dw_in),
+                         N.f32(t['sc0']) if expand else None, N.f32(t['sh0']) if expand else None,
+                         N.f32(t['rm0'], 'mean') if expand else None, N.f32(t['rs0']) if expand else None,
+                         N.f32(t['wkkc']), N.f32(dxe), N.f32(dWd), N.f32(dg1), N.f32(db1), N.f32(dg0), N.f32(db0),
+                         1.0 / (Ho * Wo), B, H, W, C, k, s, cfg['pad_t'], cfg['pad_l'], Ho, Wo)
+        N.call('effdet_dwconv_bwd_fused', x, ba, nbytes=4.0 * (2 * z1.numel() + 2 * dxe.numel()))
         grads = []
-        if cfg['expand']:
+        if expand:
             We = P[0]
-            dz0, dg0, db0 = bnact_bwd(da0, t['z0'], t['sc0'], t['sh0'], t['rm0'], t['rs0'], ACT_SWISH)
-            dWe = zb[6]
-            conv_wgrad(x, dz0, dWe, None, 1, tc=tc_enabled())
+            dWe = zb[8]
+            conv_wgrad(x, dxe, dWe, None, 1, tc=tc_enabled())
             _, wed = pack_conv(We)
-            dx = conv2d(dz0, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
+            dx = conv2d(dxe, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
             grads += [dWe, dg0, db0, None, None]
         else:
-            dx = add(da0, dy) if cfg['skip'] else da0
+            dx = add(dxe, dy) if cfg['skip'] else dxe
         grads += [dWd, dg1, db1, None, None, dWr, dbr, dWx, dbx, dWp, dg2, db2, None, None]
         ctx.t = None
         return (dx, None, None) + tuple(grads)

@@ -71,6 +71,10 @@ typedef struct {
     const void* w_tc;      /* optional bf16 hi/lo planes from effdet_pack_conv_weight_tc: when set (and the
                               epilogue needs only bias/act/residual/mask) the layer runs on the tcgen05
                               tensor cores as a bf16x3 split-precision implicit GEMM (~2^-16 per product) */
+    const float* in_scale; const float* in_shift; /* [Cin] or both NULL: the input is a RAW conv output and the
+                              operand is swish(x*in_scale+in_shift) (eval-BN + swish applied while the tile is
+                              staged, so the activated tensor never exists in HBM: MemoryEfficientSwish keeps
+                              only the pre-activation too, models/utils.py:31-42); applied before a_scale */
 } effdet_conv_args;
 int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream);
 /* The same convolution (shared w / w_tc / bias / act, channels, ksize) applied to `nlevels` (<= 8) feature maps of
@@ -93,6 +97,8 @@ typedef struct {
     void* ws_x;            /* precision 1: bf16 workspaces for the pre-split operands, */
     void* ws_dy;           /*   2*B*H*W*kpad(Cin) resp. 2*B*H*W*kpad(Cout) elements (TMA-fed kernel);
                               NULL -> the gather-producer tensor-core kernel is used instead */
+    const float* in_scale; const float* in_shift; /* [Cin] or both NULL: x is a raw conv output, the operand is
+                              swish(x*in_scale+in_shift)*a_scale (see effdet_conv_args) */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
 /* Weight gradient of one shared-weight layer accumulated over `nlevels` feature maps in one launch (all levels
@@ -119,6 +125,7 @@ int effdet_colsum(const float* x, float* out, int64_t M, int N, int device, effd
  * Stem: 3x3 stride-2 conv on the NCHW image with TF-"SAME" pad (0,1,0,1), eval-BN, swish.
  * Replaces EfficientNet.extract_features stem, models/efficientnet.py:193 (+ utils.py:126-155).
  *   x [B,3,H,W] NCHW  ->  z (raw conv) and y = swish(z*scale+shift), both [B,H/2,W/2,C0] NHWC
+ *   (y may be NULL: the consumer applies BN+swish while staging z)
  * ------------------------------------------------------------------------------------------ */
 int effdet_stem_fwd(const float* x_nchw, const float* w_oihw, const float* scale, const float* shift, float* z,
                     float* y, int B, int H, int W, int C0, int device, effdet_stream_t stream);
@@ -140,6 +147,46 @@ int effdet_dwconv_bwd_data(const float* dz, const float* w_kkc, float* dx, int B
 int effdet_dwconv_bwd_weight(const float* x, const float* dz, float* dw_c1kk, int B, int H, int W, int C, int k,
                              int stride, int pad_t, int pad_l, int Ho, int Wo, int device, effdet_stream_t stream);
 int effdet_pack_dw_weight(const float* w_c1kk, float* w_kkc, int C, int k, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Depthwise phase of MBConvBlock.forward with only PRE-activations in HBM (the reference's
+ * MemoryEfficientSwish saves the pre-activation only, models/utils.py:31-42; block: models/efficientnet.py:85-94).
+ * Pads must be the reference's static ones (models/utils.py:126-149): k3s1 1, k5s1 2, k3s2 0, k5s2 1 (top/left).
+ *   fwd: a0 = in_scale ? swish(x*in_scale+in_shift) : x        (BN0+swish applied while the tile is staged)
+ *        z  = depthwise(a0)                                    raw output, the only tensor written
+ *        se_sum[b,c] += se_alpha * sum_pixels swish(z*scale+shift)   (squeeze-excite mean, an epilogue by-product)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float* x;                                /* [B,H,W,C] raw expand-conv output z0, or the block input */
+    const float* in_scale; const float* in_shift;  /* [C] folded BN0, or both NULL (x used as is) */
+    const float* w_kkc;                            /* [k][k][C] */
+    const float* scale;    const float* shift;     /* [C] folded BN1 */
+    float* z;                                      /* [B,Ho,Wo,C] */
+    float* se_sum;                                 /* [B,C] += se_alpha * sum  (se_alpha = 1/(Ho*Wo) makes it the SE mean) */
+    int32_t B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo;
+    float se_alpha;
+} effdet_dw_fwd_args;
+int effdet_dwconv_fwd_fused(const effdet_dw_fwd_args* a, int device, effdet_stream_t stream);
+/*   bwd, one pass over the expanded tensor (replaces BN1-swish backward + depthwise weight/data gradient + BN0-swish
+ *   backward, models/utils.py:38-42 through autograd):
+ *        du1 = (dq*gate + dmean*inv_hw) * swish'(z1*scale1+shift1);  dgamma1 += sum du1*(z1-mean1)*rstd1;  dbeta1 += sum du1
+ *        dz1 = du1*scale1  (kept on chip);  da0 = depthwise^T(dz1);  dw[c,ky,kx] += sum a0 * dz1
+ *        scale0 ? { du0 = da0*swish'(x*scale0+shift0); dgamma0, dbeta0 += ...; dx = du0*scale0 } : dx = da0 */
+typedef struct {
+    const float* dq;       /* [B,Ho,Wo,C] gradient w.r.t. (a1*gate), i.e. the project conv's data gradient */
+    const float* z1;       /* [B,Ho,Wo,C] raw depthwise output */
+    const float* gate;     const float* dmean;   /* [B,C] SE gate, gradient w.r.t. the SE mean */
+    const float* scale1;   const float* shift1;  const float* mean1;  const float* rstd1;   /* [C] BN1 */
+    const float* x;        /* [B,H,W,C] raw z0 (scale0 != NULL) or the block input */
+    const float* scale0;   const float* shift0;  const float* mean0;  const float* rstd0;   /* [C] BN0 or all NULL */
+    const float* w_kkc;    /* [k][k][C] */
+    float* dx;             /* [B,H,W,C] */
+    float* dw;             /* [C,1,k,k] += */
+    float* dgamma1; float* dbeta1; float* dgamma0; float* dbeta0;   /* [C] += (BN0 ones may be NULL without BN0) */
+    float inv_hw;          /* 1/(Ho*Wo) */
+    int32_t B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo;
+} effdet_dw_bwd_args;
+int effdet_dwconv_bwd_fused(const effdet_dw_bwd_args* a, int device, effdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of  y = act(BN_eval(z)) [* row_scale]  with frozen statistics but trainable affine
@@ -178,6 +225,10 @@ int effdet_relu_bwd(const float* dy, const float* y, float* dz, int64_t n, int d
  * ------------------------------------------------------------------------------------------ */
 int effdet_spatial_reduce(const float* a, const float* b2, float* out, float alpha, int B, int HW, int C,
                           int device, effdet_stream_t stream);
+/*   effdet_spatial_reduce_act : out[b,c] += alpha * sum_hw a[b,hw,c] * swish(z[b,hw,c]*scale[c]+shift[c])
+ *   (gradient w.r.t. the SE gate from the raw depthwise output: the activated tensor is recomputed, not stored) */
+int effdet_spatial_reduce_act(const float* a, const float* z, const float* scale, const float* shift, float* out,
+                              float alpha, int B, int HW, int C, int device, effdet_stream_t stream);
 int effdet_se_gate_fwd(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
                        float* s_pre, float* gate, int B, int C, int S, int device, effdet_stream_t stream);
 int effdet_se_gate_bwd(const float* dgate, const float* mean, const float* s_pre, const float* gate,

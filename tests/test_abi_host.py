@@ -35,14 +35,34 @@ def test_shared_object_exports_every_declared_symbol(native):
     assert lib.effdet_conv_tc_kpad(36) == 64 and lib.effdet_conv_tc_kpad(720) == 768
 
 
-def test_ctypes_struct_layout_matches_header(native):
+def test_ctypes_struct_layout_matches_header(native, tmp_path):
+    """every ctypes.Structure mirrors its C struct: a C program compiled from include/effdet_b200.h with gcc prints
+    sizeof and the offset of every field, which must equal what ctypes computes for the Python-side declaration"""
     import ctypes
-    # pointer/int64 fields first, int32 tail: sizes as the C compiler lays them out on LP64
-    assert ctypes.sizeof(native.ConvArgs) == 15 * 8 + 7 * 4 + 4 + 8
-    assert ctypes.sizeof(native.WgradArgs) == 7 * 8 + 7 * 4 + 4 + 2 * 8
-    assert ctypes.sizeof(native.BnActBwdArgs) == 12 * 8 + 4 + 4 * 4 + 4
-    assert ctypes.sizeof(native.FuseArgs) == 4 * 8 + 4 + 4 + 8 + 5 * 4 + 4
-    assert ctypes.sizeof(native.FuseBwdArgs) == 5 * 8 + 4 + 4 + 3 * 8 + 3 * 4 + 4 + 2 * 8 + 5 * 4 + 4
+    import subprocess
+    pairs = {'effdet_conv_args': native.ConvArgs, 'effdet_wgrad_args': native.WgradArgs,
+             'effdet_bnact_bwd_args': native.BnActBwdArgs, 'effdet_fuse_args': native.FuseArgs,
+             'effdet_fuse_bwd_args': native.FuseBwdArgs, 'effdet_dw_fwd_args': native.DwFwdArgs,
+             'effdet_dw_bwd_args': native.DwBwdArgs}
+    for extra in ('PwGemmArgs',):
+        if hasattr(native, extra):
+            pairs['effdet_pw_gemm_args'] = getattr(native, extra)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "effdet_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    inc = os.path.join(REPO, 'include')
+    subprocess.run(['gcc', '-I', inc, str(src), '-o', str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), (cname, out[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(out['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_argument_validation_and_error_plumbing(native):

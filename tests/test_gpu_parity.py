@@ -165,6 +165,114 @@ def test_conv2d_epilogue_options(use_tc):
     assert _rel(_nchw(y), torch.relu(F.conv2d(x, w)) * (res > 0)) < tol
 
 
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+@pytest.mark.parametrize('k,s,pre,C,H,W,B', [
+    (3, 1, True, 24, 20, 36, 2), (5, 1, True, 40, 16, 16, 2), (3, 2, True, 96, 32, 32, 2), (5, 2, True, 144, 24, 40, 1),
+    (3, 1, False, 32, 33, 17, 2), (5, 2, True, 20, 9, 7, 3), (3, 2, True, 16, 7, 11, 2), (5, 1, True, 1152, 8, 8, 2),
+    (3, 2, True, 1152, 8, 8, 2), (5, 1, False, 16, 40, 20, 1),
+])
+def test_dwconv_fused_forward_backward(k, s, pre, C, H, W, B):
+    """effdet_dwconv_fwd_fused / effdet_dwconv_bwd_fused (pre-activation-only MBConv depthwise phase) against torch
+    autograd on the CPU: z1, the squeeze-excite mean, and from (dq, gate, dmean) the gradients of the raw input,
+    the depthwise weight and both BatchNorm affines -- odd sizes, tile tails, stride-2 polyphase, 1152 channels."""
+    from models import _native as N
+    ops = _ops()
+    dev = _dev()
+    g = torch.Generator().manual_seed(k * 100 + s * 10 + C + H)
+    eps = 1e-3
+    pt = (k - 1) // 2 if s == 1 else (0 if k == 3 else 1)
+    total = {(3, 1): 2, (3, 2): 1, (5, 1): 4, (5, 2): 3}[(k, s)]
+    Ho, Wo = (H + total - k) // s + 1, (W + total - k) // s + 1
+    x = torch.randn(B, C, H, W, generator=g)
+    wd = torch.randn(C, 1, k, k, generator=g) / k
+    bn = [dict(g=torch.rand(C, generator=g) + 0.5, b=torch.randn(C, generator=g) * 0.3, m=torch.randn(C, generator=g) * 0.3,
+               v=torch.rand(C, generator=g) + 0.5) for _ in range(2)]
+    gate = torch.rand(B, C, generator=g)
+    dq = torch.randn(B, C, Ho, Wo, generator=g)
+    dmean = torch.randn(B, C, generator=g)
+    # ---- torch reference ----
+    xr = x.clone().requires_grad_(True)
+    wr = wd.clone().requires_grad_(True)
+    gam = [b_['g'].clone().requires_grad_(True) for b_ in bn]
+    bet = [b_['b'].clone().requires_grad_(True) for b_ in bn]
+
+    def bnf(t, i):
+        return F.batch_norm(t, bn[i]['m'], bn[i]['v'], gam[i], bet[i], False, 0.0, eps)
+    a0 = _swish(bnf(xr, 0)) if pre else xr
+    z1r = F.conv2d(F.pad(a0, (pt, total - pt, pt, total - pt)), wr, None, s, 0, 1, C)
+    a1 = _swish(bnf(z1r, 1))
+    meanr = a1.mean(dim=(2, 3))
+    ((a1 * gate[:, :, None, None] * dq).sum() + (meanr * dmean).sum()).backward()
+    # ---- kernels ----
+    def fold(i):
+        rstd = 1.0 / torch.sqrt(bn[i]['v'] + eps)
+        sc = bn[i]['g'] * rstd
+        return [t.to(dev).contiguous() for t in (sc, bn[i]['b'] - bn[i]['m'] * sc, bn[i]['m'], rstd)]
+    sc0, sh0, mu0, rs0 = fold(0)
+    sc1, sh1, mu1, rs1 = fold(1)
+    xd = _nhwc(x)
+    wkkc = wd.view(C, k * k).t().contiguous().to(dev)
+    z1 = torch.empty(B, Ho, Wo, C, device=dev)
+    mean = torch.zeros(B, C, device=dev)
+    fa = N.DwFwdArgs(N.f32(xd), N.f32(sc0) if pre else None, N.f32(sh0) if pre else None, N.f32(wkkc), N.f32(sc1), N.f32(sh1),
+                     N.f32(z1), N.f32(mean), B, H, W, C, k, s, pt, pt, Ho, Wo, 1.0 / (Ho * Wo))
+    N.call('effdet_dwconv_fwd_fused', xd, fa)
+    assert _rel(_nchw(z1), z1r.detach()) < TOL_EXACT
+    assert _rel(mean.cpu(), meanr.detach()) < TOL_EXACT
+    dqd, gated, dmd = _nhwc(dq), gate.to(dev), dmean.to(dev)
+    dx = torch.full((B, H, W, C), float('nan'), device=dev)
+    dw = torch.zeros(C, 1, k, k, device=dev)
+    dgb = torch.zeros(4, C, device=dev)
+    ba = N.DwBwdArgs(N.f32(dqd), N.f32(z1), N.f32(gated), N.f32(dmd), N.f32(sc1), N.f32(sh1), N.f32(mu1), N.f32(rs1), N.f32(xd),
+                     N.f32(sc0) if pre else None, N.f32(sh0) if pre else None, N.f32(mu0) if pre else None,
+                     N.f32(rs0) if pre else None, N.f32(wkkc), N.f32(dx), N.f32(dw), N.f32(dgb[0]), N.f32(dgb[1]),
+                     N.f32(dgb[2]) if pre else None, N.f32(dgb[3]) if pre else None, 1.0 / (Ho * Wo), B, H, W, C, k, s, pt, pt,
+                     Ho, Wo)
+    N.call('effdet_dwconv_bwd_fused', xd, ba)
+    errs = dict(dx=_rel(_nchw(dx), xr.grad), dw=_rel(dw.cpu(), wr.grad), dg1=_rel(dgb[0].cpu(), gam[1].grad),
+                db1=_rel(dgb[1].cpu(), bet[1].grad))
+    if pre:
+        errs.update(dg0=_rel(dgb[2].cpu(), gam[0].grad), db0=_rel(dgb[3].cpu(), bet[0].grad))
+    assert max(errs.values()) < TOL_EXACT, errs
+    # gradient w.r.t. the SE gate with the activation recomputed from the raw tensor
+    dgate = torch.zeros(B, C, device=dev)
+    N.call('effdet_spatial_reduce_act', xd, N.f32(dqd), N.f32(z1), N.f32(sc1), N.f32(sh1), N.f32(dgate), 1.0, B, Ho * Wo, C)
+    want = (dq * a1.detach()).sum(dim=(2, 3))
+    assert _rel(dgate.cpu(), want) < TOL_EXACT
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [(2, 16, 16, 96, 24), (1, 12, 20, 144, 40), (2, 8, 8, 1152, 192), (3, 9, 7, 32, 16)])
+def test_conv1x1_input_prologue(B, H, W, Cin, Cout, prec):
+    """project conv of the pre-activation-only MBConv: operand = swish(bn(z)) * gate built while the tile is staged
+    (effdet_conv_args.in_scale/in_shift/a_scale), forward and weight gradient, both precisions"""
+    ops = _ops()
+    dev = _dev()
+    g = torch.Generator().manual_seed(B + Cin + Cout)
+    z = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    sc, sh = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.3
+    gate = torch.rand(B, Cin, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    a = _swish(z * sc[None, :, None, None] + sh[None, :, None, None]) * gate[:, :, None, None]
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv2d(a, wr)
+    yr.backward(dy)
+    wp = torch.nn.Parameter(w.to(dev))
+    wf, _ = ops.pack_conv(wp)
+    tf = ops.tc_packs(wp)[0]
+    zd = _nhwc(z)
+    y = ops.conv2d(zd, wf, Cout, 1, a_scale=gate.to(dev), in_scale=sc.to(dev), in_shift=sh.to(dev), w_tc=tf)
+    tol = TOL_EXACT if prec == 'fp32' else TOL_TC
+    assert _rel(_nchw(y), yr.detach()) < tol
+    dw = torch.zeros(Cout, Cin, 1, 1, device=dev)
+    ops.conv_wgrad(zd, _nhwc(dy), dw, None, 1, a_scale=gate.to(dev), tc=ops.tc_enabled(), in_scale=sc.to(dev),
+                   in_shift=sh.to(dev))
+    assert _rel(dw.cpu(), wr.grad) < tol
+
+
 def test_layout_transposes():
     from models import _ops as ops
     x = torch.randn(3, 24, 7, 9)
@@ -543,6 +651,37 @@ def test_model_train_step_vs_reference_golden(tag, prec):
     print(tag, prec, 'worst grad rel err', worst)
     for k in ('backbone._conv_head.weight', 'backbone._bn1.weight', 'backbone._fc.weight'):
         assert params[k].grad is None
+
+
+def test_d0_512_train_mode_step_vs_oracle(prec):
+    """The mode bench.py times (reference train.py:100-102): model.train(); freeze_bn() -> drop-connect ACTIVE,
+    BatchNorm frozen, D0 at 512x512, B=4.  The CUDA torch.rand([B,1,1,1]) stream the product consumes (one draw per
+    skip block, models/utils.py:79-90) is replayed into the oracle, so forward AND backward of the drop-connect
+    path (row_scale in the project-conv epilogue and in the BN2 backward) are parity-checked: losses <= 1e-3,
+    every parameter gradient within TOL_GRAD."""
+    B = 4
+    cfg = O.make_config('efficientdet-d0', num_classes=80, W_bifpn=64, D_bifpn=2)
+    sd = O.init_state_dict(cfg, seed=0)
+    m = _build('efficientdet-d0', 80, 64, 2, sd, is_training=True)
+    m.train()
+    m.is_training = True
+    m.freeze_bn()
+    images, ann = O.synthetic_batch(B, size=512, num_classes=80, seed=1000)
+    torch.manual_seed(4321)
+    cl, rl = m([images.to(_dev()), ann.to(_dev())])
+    (cl.mean() + rl.mean()).backward()
+    torch.manual_seed(4321)
+    nskip = sum(1 for i, b in enumerate(cfg['blocks']) if b['skip'] and i > 0)
+    keeps = [torch.rand([B, 1, 1, 1], dtype=torch.float32, device=_dev()).cpu() for _ in range(nskip)]
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    sdg = _grad_sd(sd)
+    ocl, orl = O.train_forward(sdg, images, ann, cfg, keep_samples=keeps)
+    (ocl.mean() + orl.mean()).backward()
+    e_c, e_r = _rel(cl.detach().cpu(), ocl.detach()), _rel(rl.detach().cpu(), orl.detach())
+    assert e_c < TOL and e_r < TOL, (e_c, e_r)
+    worst = _compare_param_grads(m, sdg, '', tol=TOL_GRAD[prec])
+    print('d0 512 train mode', prec, 'losses', float(cl), float(rl), 'rel', e_c, e_r, 'worst grad', worst,
+          'keep draws', len(keeps))
 
 
 # ------------------------------------------------------------------------------------------------

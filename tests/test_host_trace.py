@@ -8,7 +8,7 @@ entry-point calls is checked for
     in its argument struct (batch strides included -- the head writes straight into the concatenated
     [B, 49104, K] prediction buffers),
   * the per-class call counts of one steady-state step being exactly the ones the B200 bench recorded
-    (profiles/r01_bench_final.json `kernel_breakdown`, CUDA events around every C-ABI call).
+    (profiles/r02_bench_final.json `kernel_breakdown`, CUDA events around every C-ABI call).
 
 This is a test of the product's HOST code; the oracle is used only to make the state dict.
 """
@@ -96,6 +96,8 @@ class Recorder:
                 for f in ('bias', 'scale', 'shift'):
                     self.need(a[f], a['Cout'], name + ' ' + f)
                 self.need(a['a_scale'], a['B'] * a['Cin'], name + ' a_scale')
+                self.need(a['in_scale'], a['Cin'], name + ' in_scale'); self.need(a['in_shift'], a['Cin'], name + ' in_shift')
+                assert (a['in_scale'] is None) == (a['in_shift'] is None) and (a['in_scale'] is None or a['ksize'] == 1)
                 self.need(a['row_scale'], a['B'], name + ' row_scale')
                 self.need(a['residual'], (a['B'] - 1) * a['r_bstride'] + px * a['Cout'], name + ' residual')
                 self.need(a['mask_src'], (a['B'] - 1) * a['m_bstride'] + px * a['Cout'], name + ' mask_src')
@@ -109,6 +111,7 @@ class Recorder:
                 self.need(a['dw'], kk * a['Cin'] * a['Cout'], name + ' dw')
                 self.need(a['dbias'], a['Cout'], name + ' dbias')
                 self.need(a['a_scale'], a['B'] * a['Cin'], name + ' a_scale')
+                self.need(a['in_scale'], a['Cin'], name + ' in_scale'); self.need(a['in_shift'], a['Cin'], name + ' in_shift')
                 assert (a['ws_x'] is None) == (a['precision'] == 0) and (a['ws_dy'] is None) == (a['precision'] == 0)
         elif name in ('effdet_dwconv_fwd', 'effdet_dwconv_bwd_data', 'effdet_dwconv_bwd_weight'):
             B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo = snap[-10:]
@@ -131,6 +134,38 @@ class Recorder:
             else:
                 x, dz, dw = snap[:3]
                 self.need(x, big, 'dw x'); self.need(dz, small, 'dw dz'); self.need(dw, k * k * C, 'dw dw')
+        elif name in ('effdet_dwconv_fwd_fused', 'effdet_dwconv_bwd_fused'):
+            a = snap[0]
+            B, H, W, C, k, stride, Ho, Wo = (a[f] for f in ('B', 'H', 'W', 'C', 'k', 'stride', 'Ho', 'Wo'))
+            assert (k, stride) in ((3, 1), (3, 2), (5, 1), (5, 2))
+            # the reference's STATIC pads (models/utils.py:126-155) are compiled into the kernels
+            assert (a['pad_t'], a['pad_l']) == {(3, 1): (1, 1), (3, 2): (0, 0), (5, 1): (2, 2), (5, 2): (1, 1)}[(k, stride)]
+            total = {(3, 1): 2, (3, 2): 1, (5, 1): 4, (5, 2): 3}[(k, stride)]
+            assert Ho == (H + total - k) // stride + 1 and Wo == (W + total - k) // stride + 1 and C % 4 == 0
+            big, small = B * H * W * C, B * Ho * Wo * C
+            if name == 'effdet_dwconv_fwd_fused':
+                self.need(a['x'], big, 'dwf x'); self.need(a['z'], small, 'dwf z'); self.need(a['w_kkc'], k * k * C, 'dwf w')
+                for f in ('in_scale', 'in_shift', 'scale', 'shift'):
+                    self.need(a[f], C, 'dwf ' + f)
+                self.need(a['se_sum'], B * C, 'dwf se_sum')
+                assert (a['in_scale'] is None) == (a['in_shift'] is None) and abs(a['se_alpha'] * Ho * Wo - 1) < 1e-5
+            else:
+                self.need(a['dq'], small, 'dwb dq'); self.need(a['z1'], small, 'dwb z1')
+                self.need(a['x'], big, 'dwb x'); self.need(a['dx'], big, 'dwb dx')
+                self.need(a['gate'], B * C, 'dwb gate'); self.need(a['dmean'], B * C, 'dwb dmean')
+                self.need(a['w_kkc'], k * k * C, 'dwb w'); self.need(a['dw'], k * k * C, 'dwb dw')
+                for f in ('scale1', 'shift1', 'mean1', 'rstd1', 'dgamma1', 'dbeta1'):
+                    assert a[f] is not None
+                    self.need(a[f], C, 'dwb ' + f)
+                bn0 = [a[f] is not None for f in ('scale0', 'shift0', 'mean0', 'rstd0', 'dgamma0', 'dbeta0')]
+                assert all(bn0) or not any(bn0)
+                for f in ('scale0', 'shift0', 'mean0', 'rstd0', 'dgamma0', 'dbeta0'):
+                    self.need(a[f], C, 'dwb ' + f)
+                assert abs(a['inv_hw'] * Ho * Wo - 1) < 1e-5
+        elif name == 'effdet_spatial_reduce_act':
+            a, z, scale, shift, out, alpha, B, HW, C = snap
+            self.need(a, B * HW * C, 'reduce a'); self.need(z, B * HW * C, 'reduce z'); self.need(out, B * C, 'reduce out')
+            self.need(scale, C, 'reduce scale'); self.need(shift, C, 'reduce shift')
         elif name == 'effdet_stem_fwd':
             x, w, scale, shift, z, y, B, H, W, C0 = snap
             assert H % 2 == 0 and W % 2 == 0
@@ -218,7 +253,8 @@ def traced(monkeypatch):
 def test_train_step_call_trace_matches_the_gpu_profile(traced):
     rec, N = traced
     from models import EfficientDet
-    prof = json.load(open(os.path.join(REPO, 'profiles', 'r01_bench_final.json')))
+    prof_path = os.path.join(REPO, 'profiles', 'r02_bench_final.json')
+    prof = json.load(open(prof_path))
     assert prof['config']['workload'].startswith('EfficientDet-D0') or 'd0' in json.dumps(prof['config']).lower()
     cfg = O.make_config('efficientdet-d0', 80, 64, 2)
     m = EfficientDet(num_classes=80, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=True)
@@ -279,8 +315,9 @@ def test_scaled_variants_issue_consistent_geometry(traced, net, W, D, size):
     assert counts[0] == counts[1]
     c = counts[0]
     nblocks = len(cfg['blocks'])
-    assert c['effdet_dwconv_fwd'] == nblocks and c['effdet_dwconv_bwd_data'] == nblocks
-    assert c['effdet_dwconv_bwd_weight'] == nblocks and c['effdet_se_gate_bwd'] == nblocks
+    assert c['effdet_dwconv_fwd_fused'] == nblocks and c['effdet_dwconv_bwd_fused'] == nblocks
+    assert c['effdet_spatial_reduce_act'] == nblocks and c['effdet_se_gate_bwd'] == nblocks
+    assert c['effdet_bnact_bwd'] == nblocks + 1          # BN2 of every block + the stem; BN0/BN1 are fused away
     assert c['effdet_bifpn_fuse_fwd'] == 8 * D and c['effdet_bifpn_fuse_bwd'] == 8 * D
     assert c['effdet_focal_loss_fwd'] == 1 and c['effdet_focal_loss_bwd'] == 1 and c['effdet_stem_wgrad'] == 1
 
