@@ -14,6 +14,9 @@ namespace effdet {
 bool conv_tc_eligible(const effdet_conv_args* a);
 int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st);
 bool wgrad_tc_eligible(const effdet_wgrad_args* a);
+// persistent pointwise GEMM (pw_gemm.cu)
+bool pw_gemm_eligible(const effdet_conv_args* a);
+int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st);
 int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st, bool* dbias_done);
 
 constexpr int kBM = 128;   // output pixels per CTA
@@ -385,6 +388,7 @@ extern "C" int effdet_conv2d(const effdet_conv_args* a, int device, effdet_strea
     const long long Mll = (long long)a->B * a->H * a->W;
     EFFDET_REQUIRE(Mll < (1ll << 31), "conv2d: B*H*W too large");
     const int M = (int)Mll, HW = a->H * a->W;
+    if (pw_gemm_eligible(a)) return pw_gemm_launch(a, (cudaStream_t)stream);
     if (conv_tc_eligible(a)) return conv_tc_launch(a, (cudaStream_t)stream);
     // pick the N tile that wastes the fewest padded columns (ties -> wider tile)
     int best = 128;

@@ -18,147 +18,11 @@
 // Weight gradient: both operands are produced by the gather warps (pixels are the GEMM-K
 // dimension, so the natural NHWC rows are MN-major operands), split-K over pixel ranges with
 // fp32 atomics into the OIHW gradient.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
-#include <cuda.h>
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 namespace effdet {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// same load without the wait: lets the caller put independent global loads in flight first
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-// wait for the TMEM load and pin the registers after the wait (no use may be scheduled above it)
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    asm volatile(""
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :
-                 : "memory");
-}
-
-// Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 "version 1" (cute::UMMA::SmemDescriptor):
-//   bits [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=bf16, majors, N>>3, M>>4
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// split 8 consecutive fp32 values into 8 bf16 "hi" and 8 bf16 "lo" (x ~= hi + lo), 16 bytes each
-__device__ __forceinline__ void split8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
-    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-        const float r0 = f[2 * i] - __low2float(hh), r1 = f[2 * i + 1] - __high2float(hh);
-        const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 constexpr int kTcThreads = 192;        // weight-gradient kernels: 4 gather/epilogue warps + TMA + MMA
 constexpr int kTcProducers = 128;
@@ -179,11 +43,8 @@ struct FwdSmem {
     static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + kChan;
 };
 
-// MB = true adds the MBConv-only pieces (SE gate on the input, raw-output save, BN affine, drop-connect scale)
-// COAL = true (EXPERIMENTAL, round-2 staging, opt-in with EFFDET_B200_COAL=1, not yet run on hardware) replaces the
-// epilogue's thread-per-row global accesses (32 rows x 16 B per warp instruction = 32 half-filled sectors) by a
-// per-warp shared-memory transpose so that every warp instruction reads / writes 4 rows x 128 contiguous bytes.
-template <int BN, int STAGES, bool MB, bool COAL = false>
+// MB = true adds the MBConv-only pieces (BN+swish / SE gate on the input, raw-output save, BN affine, drop-connect scale)
+template <int BN, int STAGES, bool MB>
 __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effdet_conv_args& p, const int M, const int HW,
                                              const int kblocks, const int m0, const int n0) {
     using S = FwdSmem<BN, STAGES>;
@@ -335,67 +196,6 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
         const int ncols = min(BN, p.Cout - n0);
         const int nchunks = (ncols + 31) >> 5;
         const int c_begin = half ? (nchunks + 1) >> 1 : 0, c_end = half ? nchunks : (nchunks + 1) >> 1;
-        if constexpr (COAL) {
-            // every MMA has completed (accum_bar), so the stage buffers are free: [0,1024) image / pixel index of the
-            // CTA's 128 rows, then one 32 x 36-float transpose tile per warp (36: 16-byte aligned rows, and both the
-            // row-wise float4 writes and the transposed float4 reads are bank-conflict free per quarter warp)
-            int2* rowinfo = reinterpret_cast<int2*>(smem);
-            float* T = reinterpret_cast<float*>(smem + 1024) + warp * (32 * 36);
-            static_assert(1024 + 8 * 32 * 36 * 4 <= S::kStage, "transpose tiles must fit in one stage");
-            rowinfo[quarter * 32 + lane] = make_int2(row_ok ? b : -1, (int)pix);
-            __syncwarp();
-            const int colq = (lane & 7) * 4;
-#pragma unroll 1
-            for (int cc = c_begin; cc < c_end; ++cc) {
-                uint32_t acc[32];
-                tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
-                const int nl = cc * 32 + colq;
-                const int n = n0 + nl;
-                float4 rv[8], mv[8];
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int2 ri = rowinfo[quarter * 32 + it * 4 + (lane >> 3)];
-                    rv[it] = f4zero();
-                    mv[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (ri.x >= 0 && n < p.Cout) {
-                        if (p.residual) rv[it] = ldg4(p.residual + (long long)ri.x * p.r_bstride + (long long)ri.y * p.Cout + n);
-                        if (p.mask_src) mv[it] = ldg4(p.mask_src + (long long)ri.x * p.m_bstride + (long long)ri.y * p.Cout + n);
-                    }
-                }
-                tmem_ld32_wait(acc);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(T + lane * 36 + q * 4) =
-                        make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]), __uint_as_float(acc[q * 4 + 2]),
-                                    __uint_as_float(acc[q * 4 + 3]));
-                __syncwarp();
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = it * 4 + (lane >> 3);
-                    const int2 ri = rowinfo[quarter * 32 + row];
-                    if (ri.x < 0 || n >= p.Cout) continue;
-                    float4 v = *reinterpret_cast<const float4*>(T + row * 36 + colq);
-                    v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
-                    const long long yb = (long long)ri.x * p.y_bstride + (long long)ri.y * p.Cout + n;
-                    if (MB && p.z) st4(p.z + yb, v);
-                    if (MB) v = f4fma(v, *reinterpret_cast<const float4*>(chan + BN + nl), *reinterpret_cast<const float4*>(chan + 2 * BN + nl));
-                    if (p.act == EFFDET_ACT_RELU) {
-                        v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-                    } else if (p.act == EFFDET_ACT_SIGMOID) {
-                        v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
-                    } else if (p.act == EFFDET_ACT_SWISH) {
-                        v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
-                    }
-                    if (MB && p.row_scale) v = f4scale(v, __ldg(p.row_scale + ri.x));
-                    v = f4add(v, rv[it]);
-                    if (p.mask_src)
-                        v = make_float4(mv[it].x > 0.f ? v.x : 0.f, mv[it].y > 0.f ? v.y : 0.f, mv[it].z > 0.f ? v.z : 0.f,
-                                        mv[it].w > 0.f ? v.w : 0.f);
-                    st4(p.y + yb, v);
-                }
-                __syncwarp();                          // the next chunk overwrites T
-            }
-        } else {
         const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
         const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
         const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
@@ -442,7 +242,6 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
                 st4(p.y + ybase + n, v);
             }
         }
-        }   // !COAL
         tc_fence_before();
     } else if (warp == 8) {
         // ---------------- TMA: weight tiles (hi plane, lo plane) ---------------------------------------
@@ -490,11 +289,11 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
     }
 }
 
-template <int BN, int STAGES, bool MB, bool COAL = false>
+template <int BN, int STAGES, bool MB>
 __global__ void __launch_bounds__(kFwdThreads, (STAGES == 1 ? 2 : 1))
 conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ effdet_conv_args p, const int M, const int HW,
                const int kblocks) {
-    conv_tc_body<BN, STAGES, MB, COAL>(wmap, p, M, HW, kblocks, blockIdx.x * kTileM, blockIdx.y * BN);
+    conv_tc_body<BN, STAGES, MB>(wmap, p, M, HW, kblocks, blockIdx.x * kTileM, blockIdx.y * BN);
 }
 
 // Several pyramid levels that share one weight tensor (RetinaHead runs the same convs on P3..P7,
@@ -507,328 +306,15 @@ struct ConvMultiArgs {
     int nlevels;
 };
 
-template <int BN, int STAGES, bool COAL = false>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 conv_tc_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks) {
     const int tile = blockIdx.x;
     int l = 0;
     while (l + 1 < ma.nlevels && tile >= ma.tile_begin[l + 1]) ++l;
     const effdet_conv_args& p = ma.lv[l];
-    conv_tc_body<BN, STAGES, false, COAL>(wmap, p, p.B * p.H * p.W, p.H * p.W, kblocks, (tile - ma.tile_begin[l]) * kTileM,
+    conv_tc_body<BN, STAGES, false>(wmap, p, p.B * p.H * p.W, p.H * p.W, kblocks, (tile - ma.tile_begin[l]) * kTileM,
                                     blockIdx.y * BN);
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (round-2 staging, OFF unless EFFDET_B200_PAIR=1; not yet run on hardware):
-// CTA-pair variant of the multi-level kernel for Cout tiles of 256.  Two CTAs of a 2-cluster (one TPC) form one
-// tcgen05.mma.cta_group::2 tile of 256 pixels x 256 channels: each CTA gathers ITS 128 pixel rows of A and
-// stages only ITS 128-channel half of the weight tile, so a 64-channel k-block costs 32 KB (A) + 32 KB (B/2)
-// of L2->SM traffic per SM instead of 32 + 64 -- the weights were two thirds of the feed that caps the
-// single-CTA kernel at ~51 % tensor-pipe utilisation -- and three stages fit.
-// Protocol (after cutlass PipelineTmaUmmaAsync / SM100_TMA_2SM_LOAD / umma_arrive_multicast_2x1SM):
-//   * only the leader CTA (cluster rank 0) issues MMAs and owns the "full" barriers: its count is the
-//     8 gather warps of each CTA (the peer's arrive remotely) + the leader's TMA thread, which also posts
-//     the expected bytes of BOTH CTAs' weight halves; both TMA threads complete_tx on the leader's barrier;
-//   * "empty" and "accumulator ready" barriers exist in both CTAs at the same offset and are signalled by one
-//     multicast tcgen05.commit;
-//   * TMEM is allocated / freed by warp 8 of both CTAs with cta_group::2, bracketed by cluster barriers.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-// one commit, arrival on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// TMA tile -> this CTA's shared memory, bytes reported to the LEADER's mbarrier (shared::cluster address)
-__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-template <int STAGES>
-struct PairSmem {
-    static constexpr int kA = kTileM * 128;     // one bf16 plane of this CTA's 128 pixel rows
-    static constexpr int kB = 128 * 128;        // one bf16 plane of this CTA's 128-channel half of the weight tile
-    static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kChan = 256 * 4;       // bias of the pair's 256 output channels
-    static constexpr int kBytes = STAGES * kStage + 1024 + 256 + kChan;
-};
-
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
-conv_tc_pair_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks) {
-    using S = PairSmem<STAGES>;
-    constexpr int BN = 256;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [256] bias
-
-    // geometry of THIS CTA's 128 pixel rows (the two CTAs of a pair may sit on different pyramid levels: the
-    // weights are shared by all levels, only the gather and the output addressing are per CTA)
-    const int tile = blockIdx.x;
-    int l = 0;
-    while (l + 1 < ma.nlevels && tile >= ma.tile_begin[l + 1]) ++l;
-    const effdet_conv_args& p = ma.lv[l];
-    const bool dummy = tile >= ma.tile_begin[ma.nlevels];           // grid padded to an even number of tiles
-    const int M = dummy ? 0 : p.B * p.H * p.W, HW = p.H * p.W;
-    const int m0 = dummy ? 0 : (tile - ma.tile_begin[l]) * kTileM;
-    const int n0 = blockIdx.y * BN;
-
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int taps = p.ksize * p.ksize, pad = p.ksize / 2;
-    const int KT = taps * kblocks;
-    for (int i = threadIdx.x; i < BN; i += kFwdThreads) {
-        const int n = n0 + i;
-        chan[i] = (n < p.Cout && p.bias) ? __ldg(p.bias + n) : 0.f;
-    }
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 8 + 8 + 1);        // gather warps of both CTAs + the leader's TMA thread (leader's copy only is used)
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 8) tmem_alloc_pair<BN>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();                                // barriers of both CTAs initialised, TMEM allocated on both SMs
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t leader_full0 = mapa_cluster(smem_u32(&full_bar[0]), 0);      // stage s: + 8 * s
-
-    if (warp < 8) {
-        // ---------------- producers: im2col gather of this CTA's 128 rows + bf16 split -----------------
-        const int t = threadIdx.x;
-        const int j = t & 7;
-        long long base[4];
-        int oyx[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = i * 32 + (t >> 3);
-            const int m = m0 + r;
-            if (m < M) {
-                const int b = m / HW;
-                const int pix = m - b * HW;
-                const int oy = pix / p.W;
-                oyx[i] = (oy << 16) | (pix - oy * p.W);
-                base[i] = (long long)b * p.x_bstride;
-            } else {
-                oyx[i] = -1;
-                base[i] = 0;
-            }
-        }
-        auto load_stage = [&](int kt, float4 (&v)[8]) {
-            const int tap = kt / kblocks;
-            const int c = (kt - tap * kblocks) * kTileK + j * 8;
-            const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                v[2 * i] = f4zero();
-                v[2 * i + 1] = f4zero();
-                if (oyx[i] >= 0 && c < p.Cin) {
-                    const int iy = (oyx[i] >> 16) + ky, ix = (oyx[i] & 0xffff) + kx;
-                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                        const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
-                        v[2 * i] = ldg4(src);
-                        if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
-                    }
-                }
-            }
-        };
-        auto store_stage = [&](int kt, const float4 (&v)[8]) {
-            const int s = kt % STAGES;
-            const uint32_t ph = (kt / STAGES) & 1;
-            mbar_wait_cluster(&empty_bar[s], ph ^ 1);
-            uint8_t* a_hi = smem + s * S::kStage;
-            uint8_t* a_lo = a_hi + S::kA;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = i * 32 + (t >> 3);
-                uint4 hi, lo;
-                split8(v[2 * i], v[2 * i + 1], hi, lo);
-                const int off = r * 128 + ((j ^ (r & 7)) << 4);
-                *reinterpret_cast<uint4*>(a_hi + off) = hi;
-                *reinterpret_cast<uint4*>(a_lo + off) = lo;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(leader_full0 + 8 * s);
-        };
-        float4 va[8], vb[8];
-        load_stage(0, va);
-        for (int kt = 0; kt < KT; kt += 2) {
-            if (kt + 1 < KT) load_stage(kt + 1, vb);
-            store_stage(kt, va);
-            if (kt + 1 < KT) {
-                if (kt + 2 < KT) load_stage(kt + 2, va);
-                store_stage(kt + 1, vb);
-            }
-        }
-        // ---------------- epilogue: this CTA's 128 rows x 256 channels ---------------------------------
-        mbar_wait_cluster(accum_bar, 0);
-        tc_fence_after();
-        const int quarter = warp & 3, half = warp >> 2;
-        const int m = m0 + quarter * 32 + lane;
-        const bool row_ok = m < M;
-        int b = 0;
-        long long pix = 0;
-        if (row_ok) {
-            b = m / HW;
-            pix = m - b * HW;
-        }
-        const int ncols = min(BN, p.Cout - n0);
-        const int nchunks = (ncols + 31) >> 5;
-        const int c_begin = half ? (nchunks + 1) >> 1 : 0, c_end = half ? nchunks : (nchunks + 1) >> 1;
-        const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
-        const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
-        const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
-#pragma unroll 1
-        for (int cc = c_begin; cc < c_end; ++cc) {
-            uint32_t acc[32];
-            tmem_ld32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + cc * 32, acc);
-            float4 rv[8], mv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int n = n0 + cc * 32 + q * 4;
-                rv[q] = f4zero();
-                mv[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (row_ok && n < p.Cout) {
-                    if (p.residual) rv[q] = ldg4(p.residual + rbase + n);
-                    if (p.mask_src) mv[q] = ldg4(p.mask_src + mbase + n);
-                }
-            }
-            tmem_ld32_wait(acc);
-            if (!row_ok) continue;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int nl = cc * 32 + q * 4;
-                const int n = n0 + nl;
-                if (n >= p.Cout) break;
-                float4 v = make_float4(__uint_as_float(acc[q * 4]), __uint_as_float(acc[q * 4 + 1]),
-                                       __uint_as_float(acc[q * 4 + 2]), __uint_as_float(acc[q * 4 + 3]));
-                v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
-                if (p.act == EFFDET_ACT_RELU) {
-                    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-                } else if (p.act == EFFDET_ACT_SIGMOID) {
-                    v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
-                } else if (p.act == EFFDET_ACT_SWISH) {
-                    v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
-                }
-                v = f4add(v, rv[q]);
-                if (p.mask_src)
-                    v = make_float4(mv[q].x > 0.f ? v.x : 0.f, mv[q].y > 0.f ? v.y : 0.f, mv[q].z > 0.f ? v.z : 0.f,
-                                    mv[q].w > 0.f ? v.w : 0.f);
-                st4(p.y + ybase + n, v);
-            }
-        }
-        tc_fence_before();
-    } else if (warp == 8) {
-        // ---------------- TMA: this CTA's 128-channel half of the weight tile (hi plane, lo plane) ------
-        if (lane == 0) {
-            const int nhalf = n0 + (int)rank * 128;
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (kt / STAGES) & 1;
-                mbar_wait_cluster(&empty_bar[s], ph ^ 1);
-                uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
-                const uint32_t bar = leader_full0 + 8 * s;
-                if (leader) mbar_arrive_expect_tx_cluster(bar, 4 * S::kB);      // both halves, both planes
-                tma_load_3d_pair(b_hi, &wmap, bar, kt * kTileK, nhalf, 0);
-                tma_load_3d_pair(b_hi + S::kB, &wmap, bar, kt * kTileK, nhalf, 1);
-            }
-        }
-    } else {
-        // ---------------- MMA issue: leader CTA only, M = 256 over the pair -----------------------------
-        if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(2 * kTileM, BN, 0, 0);
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (kt / STAGES) & 1;
-                mbar_wait_cluster(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
-                const uint32_t a_lo = a_hi + S::kA;
-                const uint32_t b_hi = a_hi + 2 * S::kA;
-                const uint32_t b_lo = b_hi + S::kB;
-#pragma unroll
-                for (int k = 0; k < kTileK / 16; ++k) {
-                    const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
-                    const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024), dbl = umma_desc(b_lo + k * 32, 16, 1024);
-                    umma_bf16_pair(tmem_base, dal, dbh, idesc, (kt | k) != 0);
-                    umma_bf16_pair(tmem_base, dah, dbl, idesc, 1);
-                    umma_bf16_pair(tmem_base, dah, dbh, idesc, 1);
-                }
-                umma_commit_pair(&empty_bar[s], 3);
-            }
-            umma_commit_pair(accum_bar, 3);
-        }
-    }
-    tc_fence_before();
-    __syncwarp();                                      // lanes 1..31 of the TMA / MMA warps rejoin lane 0 before the aligned barrier
-    cluster_sync_all();                                // nobody frees TMEM / exits while the pair still works
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc_pair<BN>(tmem_base);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -990,11 +476,7 @@ wgrad_tc_kernel(const effdet_wgrad_args p, const int M, const int HW, const int 
 // MMAs, four warps drain TMEM into the OIHW gradient with atomics.  A stage covers a box of
 // kstage = Wb*Hb*Bb pixels (<= 64, multiple of 16).
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
+EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static bool tried = false;
     if (!tried) {
@@ -1271,162 +753,6 @@ wgrad_tc2_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constan
     }
 }
 
-// EXPERIMENTAL (round-2 staging, OFF unless EFFDET_B200_PAIR=1; not yet run on hardware): CTA-pair variant of
-// wgrad_tc2_multi_kernel<256>.  One cta_group::2 tile = 256 output channels x 256 input channels; CTA r of the pair
-// stages the dy planes of ITS 128 output channels (rows of D) and the x planes of ITS 128 input channels (half of the
-// N operand), i.e. 64 KB per 64-pixel stage instead of 96 KB, three stages.  Barrier protocol as in
-// conv_tc_pair_multi_kernel; everything is TMA-fed, so the leader's "full" barrier has a single arrival.
-__device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
-                                                 int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-
-template <int STAGES>
-struct WgPairSmem {
-    static constexpr int kA = kTileK * 128 * 2;     // one plane of this CTA's dy tile: 2 groups of 64 output channels
-    static constexpr int kB = kTileK * 128 * 2;     // one plane of this CTA's x half: 2 groups of 64 input channels
-    static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kBytes = STAGES * kStage + 1024 + 256;
-};
-
-template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-wgrad_tc2_pair_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgMultiArgs a, const int chunks_per_split,
-                            const int ctiles) {
-    using S = WgPairSmem<STAGES>;
-    constexpr int BC = 256;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pairid = blockIdx.x >> 1;
-    const int ct = pairid % ctiles, nt = pairid / ctiles;
-    const int c0 = ct * BC;                                // the pair's 256 input channels (columns of D)
-    const int n0 = nt * 2 * kTileM + (int)rank * kTileM;   // this CTA's 128 output channels (rows of D)
-    const int chalf = c0 + (int)rank * 128;                // this CTA's half of the N operand
-    const int tap = blockIdx.y;
-    const int pad = a.ksize / 2;
-    const int dy = tap / a.ksize - pad, dx = tap % a.ksize - pad;
-    const int nchunks = a.chunk_begin[a.nlevels];
-    const int ch_begin = blockIdx.z * chunks_per_split;
-    const int ch_end = min(nchunks, ch_begin + chunks_per_split);
-    const int KT = ch_end - ch_begin;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(accum_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 4) tmem_alloc_pair<BC>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t leader_full0 = mapa_cluster(smem_u32(&full_bar[0]), 0);
-    constexpr int GROUP = kTileK * 128;
-
-    if (warp == 4) {
-        if (lane == 0) {
-            int l = 0;
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (kt / STAGES) & 1;
-                const int chg = ch_begin + kt;
-                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
-                const WgGeom& g = a.g[l];
-                int ch = chg - a.chunk_begin[l];
-                const int bx = ch % g.nbx;
-                ch /= g.nbx;
-                const int by = ch % g.nby;
-                const int bb = ch / g.nby;
-                const int x0 = bx * g.Wb, y0 = by * g.Hb, b0 = bb * g.Bb;
-                const uint32_t bytes_cta = (uint32_t)(2 * (2 + 2) * g.kstage * 128);
-                mbar_wait_cluster(&empty_bar[s], ph ^ 1);
-                const uint32_t bar = leader_full0 + 8 * s;
-                if (leader) mbar_arrive_expect_tx_cluster(bar, 2 * bytes_cta);
-                uint8_t* a_hi = smem + s * S::kStage;
-                uint8_t* b_hi = a_hi + 2 * S::kA;
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        tma_load_5d_pair(a_hi + pl * S::kA + q * GROUP, &maps.dy[l], bar, n0 + q * 64, x0, y0, b0, pl);
-#pragma unroll
-                    for (int q = 0; q < 2; ++q)
-                        tma_load_5d_pair(b_hi + pl * S::kB + q * GROUP, &maps.x[l], bar, chalf + q * 64, x0 + dx, y0 + dy, b0, pl);
-                }
-            }
-        }
-    } else if (warp == 5) {
-        if (leader && lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(2 * kTileM, BC, 1, 1);
-            constexpr uint32_t LBO = GROUP, SBO = 1024;
-            int l = 0;
-            for (int kt = 0; kt < KT; ++kt) {
-                const int s = kt % STAGES;
-                const uint32_t ph = (kt / STAGES) & 1;
-                const int chg = ch_begin + kt;
-                while (l + 1 < a.nlevels && chg >= a.chunk_begin[l + 1]) ++l;
-                const int ksteps = a.g[l].kstage / 16;
-                mbar_wait_cluster(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * S::kStage);
-                const uint32_t a_lo = a_hi + S::kA;
-                const uint32_t b_hi = a_hi + 2 * S::kA;
-                const uint32_t b_lo = b_hi + S::kB;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t ko = k * 2 * SBO;
-                    const uint64_t dah = umma_desc(a_hi + ko, LBO, SBO), dal = umma_desc(a_lo + ko, LBO, SBO);
-                    const uint64_t dbh = umma_desc(b_hi + ko, LBO, SBO), dbl = umma_desc(b_lo + ko, LBO, SBO);
-                    umma_bf16_pair(tmem_base, dal, dbh, idesc, (kt | k) != 0);
-                    umma_bf16_pair(tmem_base, dah, dbl, idesc, 1);
-                    umma_bf16_pair(tmem_base, dah, dbh, idesc, 1);
-                }
-                umma_commit_pair(&empty_bar[s], 3);
-            }
-            umma_commit_pair(accum_bar, 3);
-        }
-    } else {
-        if (KT > 0) {
-            mbar_wait_cluster(accum_bar, 0);
-            tc_fence_after();
-            const int n = n0 + warp * 32 + lane;
-            const int kk = a.ksize * a.ksize;
-#pragma unroll 1
-            for (int cc = 0; cc < BC / 32; ++cc) {
-                uint32_t acc[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + cc * 32, acc);
-                if (n >= a.Cout) continue;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int c = c0 + cc * 32 + q;
-                    if (c < a.Cin) atomicAdd(a.dw + ((long long)n * a.Cin + c) * kk + tap, __uint_as_float(acc[q]));
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    tc_fence_before();
-    __syncwarp();
-    cluster_sync_all();
-    if (warp == 4) {
-        tc_fence_after();
-        tmem_dealloc_pair<BC>(tmem_base);
-    }
-}
-
 // fp32 [B][HW][C] (image stride bstride) -> bf16 planes [2][B*HW][Cpad], zero padded channels
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long long bstride, const float* __restrict__ a_scale,
                                                            __nv_bfloat16* __restrict__ out, int B, int HW, int C, int Cpad,
@@ -1570,16 +896,6 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 
 
-// round-2 staging switches: compiled, never run on hardware -> opt-in only
-static bool env_flag(const char* name) {
-    const char* v = getenv(name);
-    return v && v[0] == '1';
-}
-static bool coalesced_epilogue_enabled() {
-    static const bool on = env_flag("EFFDET_B200_COAL");
-    return on;
-}
-
 bool conv_tc_eligible(const effdet_conv_args* a) {
     if (a->w_tc == nullptr || a->Cin % 4 || a->Cout % 4 || a->Cout < 16) return false;
     // measured (profiles/r01_bench_full_breakdown.json): the narrowest 1x1 layers are faster on the CUDA cores
@@ -1608,23 +924,17 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
     if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): cuTensorMapEncodeTiled failed (%d)", (int)r);
     dim3 grid(cdiv(M, kTileM), cdiv(a->Cout, BN));
     const bool mb = a->a_scale || a->z || a->scale || a->row_scale || a->in_scale;
-    const bool coal = coalesced_epilogue_enabled();
-#define EFFDET_TC_LAUNCH1(BN_, ST_, MB_, CO_)                                                                              \
+#define EFFDET_TC_LAUNCH1(BN_, ST_, MB_)                                                                                   \
     do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN_, ST_, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                              FwdSmem<BN_, ST_>::kBytes);                                                  \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(tc): smem opt-in: %s", cudaGetErrorString(e));       \
-        conv_tc_kernel<BN_, ST_, MB_, CO_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks); \
+        conv_tc_kernel<BN_, ST_, MB_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, *a, M, HW, kblocks);      \
     } while (0)
 #define EFFDET_TC_LAUNCH(BN_, ST_)                                                                                         \
     do {                                                                                                                  \
-        if (coal) {                                                                                                       \
-            if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true, true);                                                              \
-            else EFFDET_TC_LAUNCH1(BN_, ST_, false, true);                                                                \
-        } else {                                                                                                          \
-            if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true, false);                                                             \
-            else EFFDET_TC_LAUNCH1(BN_, ST_, false, false);                                                               \
-        }                                                                                                                 \
+        if (mb) EFFDET_TC_LAUNCH1(BN_, ST_, true);                                                                        \
+        else EFFDET_TC_LAUNCH1(BN_, ST_, false);                                                                          \
     } while (0)
     // short reductions (1x1 convs of the backbone): single-stage instances so 2-3 CTAs share an SM and hide each
     // other's prologue / epilogue; long reductions: deep pipelines, one CTA per SM
@@ -1643,15 +953,6 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
 }
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g);
-
-// round-2 staging switch: the CTA-pair kernel has been compiled but never run on hardware -> opt-in only
-static bool pair_enabled() {
-    static const bool on = [] {
-        const char* v = getenv("EFFDET_B200_PAIR");
-        return v && v[0] == '1';
-    }();
-    return on;
-}
 
 int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
@@ -1680,38 +981,17 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
         tiles += cdiv((long long)levels[l].B * levels[l].H * levels[l].W, kTileM);
     }
     for (int l = nlevels; l <= kMaxLevels; ++l) ma.tile_begin[l] = tiles;
-    if (BN == 256 && pair_enabled()) {
-        // experimental CTA-pair kernel: same tiles, grid padded to whole pairs, weight box = one 128-channel half
-        CUtensorMap hmap;
-        const cuuint32_t hbox[3] = {(cuuint32_t)kTileK, 128, 1};
-        r = enc(&hmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_tc), gdim, gstr, hbox, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc pair): cuTensorMapEncodeTiled failed (%d)", (int)r);
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_multi_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             PairSmem<3>::kBytes);
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc pair): smem opt-in: %s", cudaGetErrorString(e));
-        dim3 pgrid((tiles + 1) / 2 * 2, cdiv(a->Cout, 256));
-        conv_tc_pair_multi_kernel<3><<<pgrid, kFwdThreads, PairSmem<3>::kBytes, st>>>(hmap, ma, kblocks);
-        return launch_status("conv_tc_pair_multi_kernel");
-    }
     dim3 grid(tiles, cdiv(a->Cout, BN));
-#define EFFDET_TCM_LAUNCH1(BN_, ST_, CO_)                                                                                  \
-    do {                                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_multi_kernel<BN_, ST_, CO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             FwdSmem<BN_, ST_>::kBytes);                                                  \
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): smem opt-in: %s", cudaGetErrorString(e)); \
-        conv_tc_multi_kernel<BN_, ST_, CO_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks);      \
-    } while (0)
 #define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
     do {                                                                                                                  \
-        if (coalesced_epilogue_enabled()) EFFDET_TCM_LAUNCH1(BN_, ST_, true);                                             \
-        else EFFDET_TCM_LAUNCH1(BN_, ST_, false);                                                                         \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_multi_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                             FwdSmem<BN_, ST_>::kBytes);                                                  \
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): smem opt-in: %s", cudaGetErrorString(e)); \
+        conv_tc_multi_kernel<BN_, ST_><<<grid, kFwdThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks);            \
     } while (0)
     if (BN == 64) EFFDET_TCM_LAUNCH(64, 4);
     else if (BN == 128) EFFDET_TCM_LAUNCH(128, 3);
     else EFFDET_TCM_LAUNCH(256, 2);
-#undef EFFDET_TCM_LAUNCH1
 #undef EFFDET_TCM_LAUNCH
     return launch_status("conv_tc_multi_kernel");
 }
@@ -1837,20 +1117,6 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     int cps = cdiv(chunks, splits);
     splits = cdiv(chunks, cps);
     cudaError_t e;
-    if (BC == 256 && a0->Cout >= 256 && pair_enabled()) {
-        // experimental CTA-pair kernel: 256 x 256 tiles of the weight gradient per cluster of two CTAs
-        constexpr int ST = 3;
-        const int npairs = ctiles * cdiv(a0->Cout, 2 * kTileM);
-        int ps = (148 * 2) / (npairs * 2 * taps);
-        if (ps < 1) ps = 1;
-        if (ps > cdiv(chunks, 4)) ps = cdiv(chunks, 4);
-        const int pcps = cdiv(chunks, ps);
-        ps = cdiv(chunks, pcps);
-        e = cudaFuncSetAttribute(wgrad_tc2_pair_multi_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgPairSmem<ST>::kBytes);
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad_multi(tc pair): smem opt-in: %s", cudaGetErrorString(e));
-        wgrad_tc2_pair_multi_kernel<ST><<<dim3(npairs * 2, taps, ps), kTcThreads, WgPairSmem<ST>::kBytes, st>>>(maps, ma, pcps, ctiles);
-        return launch_status("wgrad_tc2_pair_multi_kernel");
-    }
     dim3 grid(ctiles * ntiles, taps, splits);
     if (BC == 256) {
         constexpr int ST = 2;

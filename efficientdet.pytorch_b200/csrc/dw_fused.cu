@@ -42,12 +42,27 @@ struct DwGeo {
     static constexpr int BIH = TCY * S, BIW = TCX * S;
 };
 
-__device__ __forceinline__ float4 f4swish(const float4 u) {
-    return make_float4(swishf_(u.x), swishf_(u.y), swishf_(u.z), swishf_(u.w));
+// sigmoid through ex2.approx + a correctly rounded reciprocal: ~1e-6 relative (|x| * 2^-24 from the exponent scaling),
+// 5 instructions instead of ~25 for expf + IEEE division -- these kernels evaluate 2-3 sigmoids per element they move,
+// and at 8 warps per SM the instruction stream, not HBM, was the first limit.
+__device__ __forceinline__ float fsigmoid(const float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fswish(const float x) { return x * fsigmoid(x); }
+__device__ __forceinline__ float fswish_grad(const float x) {
+    const float s = fsigmoid(x);
+    return s * (1.0f + x * (1.0f - s));
 }
+__device__ __forceinline__ float4 f4swish(const float4 u) { return make_float4(fswish(u.x), fswish(u.y), fswish(u.z), fswish(u.w)); }
 __device__ __forceinline__ float4 f4swish_grad(const float4 u) {
-    return make_float4(swish_gradf_(u.x), swish_gradf_(u.y), swish_gradf_(u.z), swish_gradf_(u.w));
+    return make_float4(fswish_grad(u.x), fswish_grad(u.y), fswish_grad(u.z), fswish_grad(u.w));
 }
+// 16-byte asynchronous global->shared copy; src_bytes = 0 zero-fills the destination (halo / tail).  Every copy of a
+// tile is issued before anything waits, so a CTA has its whole tile (tens of KB) in flight at once.
+__device__ __forceinline__ void dw_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void dw_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ float4 f4sub(const float4 a, const float4 b) {
     return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
 }
@@ -99,12 +114,18 @@ __global__ void __launch_bounds__(kDwT) dw_fwd_fused_kernel(const effdet_dw_fwd_
             const int pix = i >> 2;
             const int r = pix / G::FIW, c = pix - r * G::FIW;
             const int iy = iy0 + r, ix = ix0 + c;
-            float4 v = f4zero();
-            if (cv_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-                v = ldg4(xb + ((long long)iy * p.W + ix) * p.C);
-                if (PRE) v = f4swish(f4fma(v, isc, ish));
+            const bool ok = cv_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            dw_cp_async16(&xs[pix * kPS + cvl], ok ? xb + ((long long)iy * p.W + ix) * p.C : xb, ok ? 16 : 0);
+        }
+        dw_cp_async_wait_all();
+        if (PRE) {                                       // BN0 + swish once per staged element, in place (own copies only)
+            for (int i = t; i < G::FIH * G::FIW * kCVc; i += kDwT) {
+                const int pix = i >> 2;
+                const int r = pix / G::FIW, c = pix - r * G::FIW;
+                const int iy = iy0 + r, ix = ix0 + c;
+                if (cv_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)      // padding stays zero AFTER the activation
+                    xs[pix * kPS + cvl] = f4swish(f4fma(xs[pix * kPS + cvl], isc, ish));
             }
-            xs[pix * kPS + cvl] = v;
         }
         __syncthreads();
         constexpr int NCOL = 3 * S + K;
@@ -166,8 +187,9 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
     constexpr int KK = K * K;
     constexpr int NQ = KK + 4;                           // reduced quantities: dW taps, dgamma1, dbeta1, dgamma0, dbeta0
     extern __shared__ __align__(16) float4 dwsm[];
-    float4* gs = dwsm;                                   // dz1 of the touched outputs   [GH*GW][kPS]
-    float4* as = gs + G::GH * G::GW * kPS;               // a0 = swish(bn0(z0)) (or x)   [BIH*BIW][kPS]
+    float4* gs = dwsm;                                   // dq, then dz1 of the touched outputs   [GH*GW][kPS]
+    float4* z1s = gs + G::GH * G::GW * kPS;              // raw z1 of the same outputs            [GH*GW][kPS]
+    float4* as = z1s + G::GH * G::GW * kPS;              // a0 = swish(bn0(z0)) (or x)            [BIH*BIW][kPS]
     float4* zs = as + G::BIH * G::BIW * kPS;             // raw z0 (PRE only)            [BIH*BIW][kPS]
     float4* ws = zs + (PRE ? G::BIH * G::BIW * kPS : 0); // [KK][kCVc]
     float4* red = ws + KK * kCVc;                        // [NQ][4 warps][kCVc]
@@ -199,38 +221,50 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int cy0 = ty * G::TCY, cx0 = tx * G::TCX;          // first cell (= output coordinate) of the tile
         __syncthreads();
-        // ---- stage dz1 of every output the tile's cells touch -------------------------------------------------------
+        // ---- stage the raw operands: every 16-byte copy of the tile is in flight before anything waits ---------------
         for (int i = t; i < G::GH * G::GW * kCVc; i += kDwT) {
             const int pix = i >> 2;
             const int r = pix / G::GW, c = pix - r * G::GW;
             const int oy = cy0 + r + G::DMIN, ox = cx0 + c + G::DMIN;
-            float4 v = f4zero();
-            if (cv_ok && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo) {
-                const long long off = ((long long)oy * p.Wo + ox) * p.C;
-                const float4 g = f4fma(ldg4(dqb + off), gt, dm);          // SE product rule: d(a1*gate) + d(mean)
-                const float4 z = ldg4(z1b + off);
-                const float4 du = f4mul(g, f4swish_grad(f4fma(z, sc1, sh1)));
-                const bool owned = r + G::DMIN >= 0 && r + G::DMIN < G::TCY && c + G::DMIN >= 0 && c + G::DMIN < G::TCX;
-                if (owned) {                                               // each output is counted by exactly one tile
-                    sg1 = f4fma(du, f4mul(f4sub(z, mu1), rs1), sg1);
-                    sb1 = f4add(sb1, du);
-                }
-                v = f4mul(du, sc1);
-            }
-            gs[pix * kPS + cvl] = v;
+            const bool ok = cv_ok && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo;
+            const long long off = ok ? ((long long)oy * p.Wo + ox) * p.C : 0;
+            dw_cp_async16(&gs[pix * kPS + cvl], dqb + off, ok ? 16 : 0);
+            dw_cp_async16(&z1s[pix * kPS + cvl], z1b + off, ok ? 16 : 0);
         }
-        // ---- stage the tile's input pixels: activated a0 (and raw z0 for the BN0 backward) ------------------------
         for (int i = t; i < G::BIH * G::BIW * kCVc; i += kDwT) {
             const int pix = i >> 2;
             const int r = pix / G::BIW, c = pix - r * G::BIW;
             const int iy = cy0 * S + r, ix = cx0 * S + c;
-            float4 z = f4zero(), a = f4zero();
-            if (cv_ok && iy < p.H && ix < p.W) {
-                z = ldg4(xb + ((long long)iy * p.W + ix) * p.C);
-                a = PRE ? f4swish(f4fma(z, sc0, sh0)) : z;
+            const bool ok = cv_ok && iy < p.H && ix < p.W;
+            dw_cp_async16(PRE ? &zs[pix * kPS + cvl] : &as[pix * kPS + cvl], ok ? xb + ((long long)iy * p.W + ix) * p.C : xb,
+                          ok ? 16 : 0);
+        }
+        dw_cp_async_wait_all();
+        // ---- dz1 in place of dq (each thread transforms the elements it copied itself) --------------------------------
+        for (int i = t; i < G::GH * G::GW * kCVc; i += kDwT) {
+            const int pix = i >> 2;
+            const int r = pix / G::GW, c = pix - r * G::GW;
+            const int oy = cy0 + r + G::DMIN, ox = cx0 + c + G::DMIN;
+            if (!(cv_ok && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo)) continue;     // zero-filled: contributes nothing
+            const float4 g = f4fma(gs[pix * kPS + cvl], gt, dm);              // SE product rule: d(a1*gate) + d(mean)
+            const float4 z = z1s[pix * kPS + cvl];
+            const float4 du = f4mul(g, f4swish_grad(f4fma(z, sc1, sh1)));
+            const bool owned = r + G::DMIN >= 0 && r + G::DMIN < G::TCY && c + G::DMIN >= 0 && c + G::DMIN < G::TCX;
+            if (owned) {                                                       // each output is counted by exactly one tile
+                sg1 = f4fma(du, f4mul(f4sub(z, mu1), rs1), sg1);
+                sb1 = f4add(sb1, du);
             }
-            as[pix * kPS + cvl] = a;
-            if (PRE) zs[pix * kPS + cvl] = z;
+            gs[pix * kPS + cvl] = f4mul(du, sc1);
+        }
+        // ---- activated a0 next to the raw z0 (BN0 backward needs both) --------------------------------------------------
+        if (PRE) {
+            for (int i = t; i < G::BIH * G::BIW * kCVc; i += kDwT) {
+                const int pix = i >> 2;
+                const int r = pix / G::BIW, c = pix - r * G::BIW;
+                const int iy = cy0 * S + r, ix = cx0 * S + c;
+                const bool ok = cv_ok && iy < p.H && ix < p.W;
+                as[pix * kPS + cvl] = ok ? f4swish(f4fma(zs[pix * kPS + cvl], sc0, sh0)) : f4zero();
+            }
         }
         __syncthreads();
         // ---- strips of 4 cells: data gradient, weight gradient, BN0 backward ------------------------------------------
@@ -327,7 +361,7 @@ static size_t dw_fwd_smem() {
 template <int K, int S, bool PRE>
 static size_t dw_bwd_smem() {
     using G = DwGeo<K, S>;
-    return (size_t)(G::GH * G::GW * kPS + (PRE ? 2 : 1) * G::BIH * G::BIW * kPS + K * K * kCVc +
+    return (size_t)(2 * G::GH * G::GW * kPS + (PRE ? 2 : 1) * G::BIH * G::BIW * kPS + K * K * kCVc +
                     (K * K + 4) * (kDwT / 32) * kCVc) * sizeof(float4);
 }
 

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu',
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu',
            'loss.cu', 'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']

@@ -273,6 +273,43 @@ def test_conv1x1_input_prologue(B, H, W, Cin, Cout, prec):
     assert _rel(dw.cpu(), wr.grad) < tol
 
 
+@pytest.mark.parametrize('B,H,W,Cin,Cout', [
+    (2, 64, 64, 16, 96), (1, 100, 37, 24, 144), (2, 16, 16, 144, 24), (2, 8, 8, 1152, 192), (2, 8, 8, 192, 1152),
+    (3, 20, 12, 40, 240), (2, 16, 16, 672, 112), (1, 8, 8, 320, 64), (8, 64, 64, 32, 16), (5, 48, 48, 96, 24),
+    (1, 3, 5, 80, 480), (2, 32, 32, 480, 80),
+])
+def test_pointwise_gemm_persistent_kernel(B, H, W, Cin, Cout):
+    """pw_gemm_kernel (persistent TMA-fed tcgen05 GEMM of every backbone / lateral 1x1 conv) vs torch fp32: the three
+    epilogue routes -- plain output through TMA tile stores, bias, and the MBConv project epilogue (raw-output save,
+    BN affine, drop-connect scale, residual) with direct stores -- over row tails, several n-tiles, 1..18 k-blocks
+    and more m-tiles than CTAs."""
+    ops = _ops()
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout + 11)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    rsc = torch.rand(B, generator=g) + 0.5
+    res = torch.randn(B, Cout, H, W, generator=g)
+    wp = torch.nn.Parameter(w.to(dev))
+    wf, wd = ops.pack_conv(wp)
+    tf, td = ops.pack_conv_tc(wp)
+    xd = _nhwc(x)
+    ref = F.conv2d(x, w)
+    y = ops.conv2d(xd, wf, Cout, 1, w_tc=tf)                                   # plain: TMA-store epilogue
+    assert _rel(_nchw(y), ref) < TOL_TC
+    y = ops.conv2d(xd, wf, Cout, 1, bias=bias.to(dev), w_tc=tf)                # lateral conv: + bias
+    assert _rel(_nchw(y), ref + bias[None, :, None, None]) < TOL_TC
+    y, z = ops.conv2d(xd, wf, Cout, 1, scale=sc.to(dev), shift=sh.to(dev), row_scale=rsc.to(dev), residual=_nhwc(res),
+                      save_z=True, w_tc=tf)                                    # project conv epilogue, direct stores
+    want = (ref * sc[None, :, None, None] + sh[None, :, None, None]) * rsc[:, None, None, None] + res
+    assert _rel(_nchw(z), ref) < TOL_TC and _rel(_nchw(y), want) < TOL_TC
+    dy = torch.randn(B, Cout, H, W, generator=g)                               # data gradient = same kernel, transposed pack
+    dx = ops.conv2d(_nhwc(dy), wd, Cin, 1, w_tc=td)
+    assert _rel(_nchw(dx), F.conv_transpose2d(dy, w)) < TOL_TC
+
+
 def test_layout_transposes():
     from models import _ops as ops
     x = torch.randn(3, 24, 7, 9)
