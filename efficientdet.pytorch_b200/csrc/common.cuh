@@ -26,19 +26,32 @@ inline int launch_status(const char* what) {
     return EFFDET_OK;
 }
 
-inline int use_device(int device) {
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(EFFDET_ERR_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
-    return EFFDET_OK;
-}
+// Makes `device` current for the duration of an entry point and restores the caller's current device on return
+// (a call on a tensor of another GPU must not leak a device switch into the calling thread).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    int set(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev == device) return EFFDET_OK;
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_DEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+        changed = prev >= 0;
+        return EFFDET_OK;
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
 
 #define EFFDET_REQUIRE(cond, ...)                                            \
     do {                                                                     \
         if (!(cond)) return effdet::fail(EFFDET_ERR_ARG, __VA_ARGS__);       \
     } while (0)
 #define EFFDET_DEVICE(dev)                                                   \
+    effdet::DeviceGuard _effdet_device_guard;                                \
     do {                                                                     \
-        int _s = effdet::use_device(dev);                                    \
+        int _s = _effdet_device_guard.set(dev);                              \
         if (_s) return _s;                                                   \
     } while (0)
 
@@ -51,6 +64,21 @@ __device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
 // d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))      (reference: models/utils.py:38-42)
 __device__ __forceinline__ float swish_gradf_(float x) {
     float s = sigmoidf_(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+
+// Fast sigmoid / swish for the HBM-bound kernels that evaluate an activation per element they move: ex2.approx with
+// the log2(e) scaling + rcp.approx, ~1e-6 relative (|x| * 2^-24 from the exponent scaling + 3 ulp), 4 instructions
+// instead of ~25 (with branches) for expf + IEEE division.
+__device__ __forceinline__ float fsigmoid(const float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));      // no slow path: 2 MUFU + 2 FP ops, branch-free
+    return r;
+}
+__device__ __forceinline__ float fswish(const float x) { return x * fsigmoid(x); }
+__device__ __forceinline__ float fswish_grad(const float x) {
+    const float s = fsigmoid(x);
     return s * (1.0f + x * (1.0f - s));
 }
 

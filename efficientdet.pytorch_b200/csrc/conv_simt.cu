@@ -371,7 +371,9 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
 using namespace effdet;
 
 extern "C" int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(a && a->x && a->w && a->y, "conv2d: null tensor");
+    EFFDET_REQUIRE(a && (a->x || a->x_planes) && a->w && a->y, "conv2d: null tensor");
+    EFFDET_REQUIRE(!a->x_planes || (pw_gemm_eligible(a) && aligned16(a->x_planes)),
+                   "conv2d: x_planes is only understood by the tensor-core 1x1 path (Cin %% 8 == 0, no input prologue)");
     EFFDET_REQUIRE(a->ksize == 1 || a->ksize == 3, "conv2d: ksize %d not in {1,3}", a->ksize);
     EFFDET_REQUIRE(a->Cin % 4 == 0 && a->Cout % 4 == 0, "conv2d: Cin=%d Cout=%d must be multiples of 4", a->Cin, a->Cout);
     EFFDET_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv2d: empty shape");
@@ -430,7 +432,9 @@ int effdet::colsum_launch(const float* x, float* out, long long M, int N, long l
 }
 
 extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(a && a->x && a->dy && a->dw, "wgrad: null tensor");
+    EFFDET_REQUIRE(a && a->x && (a->dy || a->dy_planes) && a->dw, "wgrad: null tensor");
+    EFFDET_REQUIRE(!a->dy_planes || (a->precision == 1 && !a->dbias && a->Cout % 8 == 0 && aligned16(a->dy_planes) && a->ws_x),
+                   "wgrad: dy_planes needs precision 1, no dbias, Cout %% 8 == 0 and the ws_x workspace");
     EFFDET_REQUIRE(a->ksize == 1 || a->ksize == 3, "wgrad: ksize %d not in {1,3}", a->ksize);
     EFFDET_REQUIRE(a->Cin % 4 == 0 && a->Cout % 4 == 0, "wgrad: channels must be multiples of 4");
     EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->dy) && aligned16(a->a_scale) && aligned16(a->in_scale) && aligned16(a->in_shift),
@@ -448,6 +452,9 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     bool dbias_done = false;
     if (wgrad_tc_eligible(a)) {
         s = wgrad_tc_launch(a, st, &dbias_done);
+    } else if (a->dy_planes) {
+        return fail(EFFDET_ERR_UNSUPPORTED, "wgrad: dy_planes given but the TMA-fed tensor-core kernel cannot take this shape "
+                                            "(check effdet_wgrad_tc_geometry_ok first)");
     } else {
     int BC, BN;
     if (a->Cin <= 32) { BC = 32; BN = 128; }

@@ -999,8 +999,8 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
 bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
     if (a->precision != 1 || a->Cin % 4 || a->Cout % 4 || a->Cin < 16 || a->Cout < 16) return false;
     WgGeom g;
-    const bool tma_ok = a->ws_x && a->ws_dy && wg_geometry(a->B, a->H, a->W, &g);
-    return tma_ok || (!a->a_scale && !a->in_scale);     // the gather-producer fallback has no input prologue
+    const bool tma_ok = a->ws_x && (a->ws_dy || a->dy_planes) && wg_geometry(a->B, a->H, a->W, &g);
+    return tma_ok || (!a->a_scale && !a->in_scale && !a->dy_planes);     // the gather-producer fallback has no input prologue
 }
 
 static bool wg_geometry(int B, int H, int W, WgGeom* g) {
@@ -1036,7 +1036,7 @@ static int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, in
 static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     WgGeom g;
     EncodeTiledFn enc = encode_fn();
-    if (!enc || !a->ws_x || !a->ws_dy || !wg_geometry(a->B, a->H, a->W, &g)) return 1;
+    if (!enc || !a->ws_x || !(a->ws_dy || a->dy_planes) || !wg_geometry(a->B, a->H, a->W, &g)) return 1;
     const int HW = a->H * a->W;
     const int cin_pad = conv_tc_kpad(a->Cin), cout_pad = conv_tc_kpad(a->Cout);
     int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
@@ -1045,9 +1045,13 @@ static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
                                                 a->in_scale, a->in_shift);
     int s = launch_status("split_planes_kernel");
     if (s) return s;
-    if ((s = split_dy_launch(a, cout_pad, st))) return s;      // also accumulates the bias gradient
     CUtensorMap mdy, mx;
-    if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;
+    if (a->dy_planes) {        // dy arrives pre-split (unpadded pitch; TMA zero-fills the channels beyond Cout)
+        if ((s = planes_map(enc, &mdy, const_cast<void*>(a->dy_planes), a->B, a->H, a->W, a->Cout, g))) return s;
+    } else {
+        if ((s = split_dy_launch(a, cout_pad, st))) return s;      // also accumulates the bias gradient
+        if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;
+    }
     if ((s = planes_map(enc, &mx, a->ws_x, a->B, a->H, a->W, cin_pad, g))) return s;
     const int taps = a->ksize * a->ksize;
     const int BC = a->Cin > 64 ? 256 : 64;
@@ -1087,7 +1091,7 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     int chunks = 0;
     for (int l = 0; l < nlevels; ++l) {
         const effdet_wgrad_args* a = &levels[l];
-        if (!a->ws_x || !a->ws_dy || a->a_scale || a->in_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
+        if (!a->ws_x || !a->ws_dy || a->dy_planes || a->a_scale || a->in_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
         ma.chunk_begin[l] = chunks;
         chunks += ma.g[l].nbx * ma.g[l].nby * ma.g[l].nbb;
     }
@@ -1171,6 +1175,10 @@ int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st, bool* dbias_don
 using namespace effdet;
 
 extern "C" int effdet_conv_tc_kpad(int channels) { return conv_tc_kpad(channels); }
+extern "C" int effdet_wgrad_tc_geometry_ok(int B, int H, int W) {
+    WgGeom g;
+    return wg_geometry(B, H, W, &g) ? 1 : 0;
+}
 
 namespace effdet {   // defined in conv_simt.cu
 int colsum_launch(const float* x, float* out, long long M, int N, long long HW, long long bstride, int device,

@@ -20,6 +20,8 @@
 // correlation with the taps of matching parity), so no thread ever tests divisibility at run time.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace effdet {
 
 constexpr int kDwT = 128;       // threads per CTA
@@ -42,15 +44,6 @@ struct DwGeo {
     static constexpr int BIH = TCY * S, BIW = TCX * S;
 };
 
-// sigmoid through ex2.approx + a correctly rounded reciprocal: ~1e-6 relative (|x| * 2^-24 from the exponent scaling),
-// 5 instructions instead of ~25 for expf + IEEE division -- these kernels evaluate 2-3 sigmoids per element they move,
-// and at 8 warps per SM the instruction stream, not HBM, was the first limit.
-__device__ __forceinline__ float fsigmoid(const float x) { return __frcp_rn(1.0f + __expf(-x)); }
-__device__ __forceinline__ float fswish(const float x) { return x * fsigmoid(x); }
-__device__ __forceinline__ float fswish_grad(const float x) {
-    const float s = fsigmoid(x);
-    return s * (1.0f + x * (1.0f - s));
-}
 __device__ __forceinline__ float4 f4swish(const float4 u) { return make_float4(fswish(u.x), fswish(u.y), fswish(u.z), fswish(u.w)); }
 __device__ __forceinline__ float4 f4swish_grad(const float4 u) {
     return make_float4(fswish_grad(u.x), fswish_grad(u.y), fswish_grad(u.z), fswish_grad(u.w));
@@ -189,7 +182,7 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
     extern __shared__ __align__(16) float4 dwsm[];
     float4* gs = dwsm;                                   // dq, then dz1 of the touched outputs   [GH*GW][kPS]
     float4* z1s = gs + G::GH * G::GW * kPS;              // raw z1 of the same outputs            [GH*GW][kPS]
-    float4* as = z1s + G::GH * G::GW * kPS;              // a0 = swish(bn0(z0)) (or x)            [BIH*BIW][kPS]
+    float4* as = z1s + G::GH * G::GW * kPS;              // sigmoid(bn0(z0)) (PRE) or a0 = x      [BIH*BIW][kPS]
     float4* zs = as + G::BIH * G::BIW * kPS;             // raw z0 (PRE only)            [BIH*BIW][kPS]
     float4* ws = zs + (PRE ? G::BIH * G::BIW * kPS : 0); // [KK][kCVc]
     float4* red = ws + KK * kCVc;                        // [NQ][4 warps][kCVc]
@@ -263,7 +256,12 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
                 const int r = pix / G::BIW, c = pix - r * G::BIW;
                 const int iy = cy0 * S + r, ix = cx0 * S + c;
                 const bool ok = cv_ok && iy < p.H && ix < p.W;
-                as[pix * kPS + cvl] = ok ? f4swish(f4fma(zs[pix * kPS + cvl], sc0, sh0)) : f4zero();
+                float4 sg = f4zero();                       // sigmoid(bn0(z0)): a0 = u*sg and swish'(u) both follow from it
+                if (ok) {
+                    const float4 q = f4fma(zs[pix * kPS + cvl], sc0, sh0);
+                    sg = make_float4(fsigmoid(q.x), fsigmoid(q.y), fsigmoid(q.z), fsigmoid(q.w));
+                }
+                as[pix * kPS + cvl] = sg;
             }
         }
         __syncthreads();
@@ -282,6 +280,8 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
                     for (int i = 0; i < 4; ++i) {
                         da[i] = f4zero();
                         a0[i] = as[(arow + i * S) * kPS + cvl];
+                        if (PRE)                              // staged: sigmoid(u) and raw z0 -> a0 = u * sigmoid(u)
+                            a0[i] = f4mul(f4fma(zs[(arow + i * S) * kPS + cvl], sc0, sh0), a0[i]);   // out of image: sigmoid staged as 0
                     }
 #pragma unroll
                     for (int ky = 0; ky < K; ++ky) {
@@ -313,12 +313,27 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
                         float4 out = da[i];
                         if (PRE) {
                             const float4 z = zs[(arow + i * S) * kPS + cvl];
-                            const float4 du = f4mul(da[i], f4swish_grad(f4fma(z, sc0, sh0)));
+                            const float4 sg = as[(arow + i * S) * kPS + cvl], uu = f4fma(z, sc0, sh0);   // swish'(u) = s * (1 + u * (1 - s))
+                            const float4 sp = make_float4(sg.x * (1.f + uu.x * (1.f - sg.x)), sg.y * (1.f + uu.y * (1.f - sg.y)),
+                                                          sg.z * (1.f + uu.z * (1.f - sg.z)), sg.w * (1.f + uu.w * (1.f - sg.w)));
+                            const float4 du = f4mul(da[i], sp);
                             sg0 = f4fma(du, f4mul(f4sub(z, mu0), rs0), sg0);
                             sb0 = f4add(sb0, du);
                             out = f4mul(du, sc0);
                         }
-                        st4(dxb + ((long long)iy * p.W + ix) * p.C, out);
+                        if (p.dx_planes) {                    // bf16 hi/lo planes: the operand format of the expand conv's
+                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(out.x, out.y), h1 = __floats2bfloat162_rn(out.z, out.w);
+                            const __nv_bfloat162 l0 = __floats2bfloat162_rn(out.x - __low2float(h0), out.y - __high2float(h0));
+                            const __nv_bfloat162 l1 = __floats2bfloat162_rn(out.z - __low2float(h1), out.w - __high2float(h1));
+                            const long long e = (((long long)b * p.H + iy) * p.W + ix) * p.C + cq;   // tensor-core gradients
+                            __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(p.dx_planes);
+                            *reinterpret_cast<uint2*>(pl + e) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+                            *reinterpret_cast<uint2*>(pl + (long long)p.B * p.H * p.W * p.C + e) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+                        } else {
+                            st4(dxb + ((long long)iy * p.W + ix) * p.C, out);
+                        }
                     }
                 }
             }
@@ -430,8 +445,9 @@ extern "C" int effdet_dwconv_fwd_fused(const effdet_dw_fwd_args* a, int device, 
 
 extern "C" int effdet_dwconv_bwd_fused(const effdet_dw_bwd_args* a, int device, effdet_stream_t stream) {
     EFFDET_REQUIRE(a && a->dq && a->z1 && a->gate && a->dmean && a->scale1 && a->shift1 && a->mean1 && a->rstd1 && a->x &&
-                       a->w_kkc && a->dx && a->dw && a->dgamma1 && a->dbeta1,
+                       a->w_kkc && (a->dx || a->dx_planes) && a->dw && a->dgamma1 && a->dbeta1,
                    "dwconv_bwd_fused: null tensor");
+    EFFDET_REQUIRE(!a->dx_planes || (a->C % 8 == 0 && aligned16(a->dx_planes)), "dwconv_bwd_fused: dx_planes needs C %% 8 == 0");
     const bool pre = a->scale0 != nullptr;
     EFFDET_REQUIRE(!pre || (a->shift0 && a->mean0 && a->rstd0 && a->dgamma0 && a->dbeta0), "dwconv_bwd_fused: BN0 tensors come together");
     EFFDET_REQUIRE(aligned16(a->dq) && aligned16(a->z1) && aligned16(a->gate) && aligned16(a->dmean) && aligned16(a->x) &&

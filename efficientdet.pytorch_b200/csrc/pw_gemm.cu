@@ -10,11 +10,13 @@
 //
 //   warp 0      TMA producer : fp32 activation boxes [128 rows x 32 channels] (SWIZZLE_128B, out-of-bounds rows / channels
 //                              zero-filled by the hardware) + the bf16 hi/lo weight tile of the k-block -> ring of NS stages
-//   warps 2-5   converters   : fp32 tile -> optional BN+swish (+ squeeze-excite gate) prologue -> bf16 hi + lo planes in the
-//                              canonical K-major SWIZZLE_128B layout (x = hi + lo to 16 mantissa bits)
+//   NC warps    converters   : fp32 tile -> optional BN+swish (+ squeeze-excite gate) prologue -> bf16 hi + lo planes in the
+//                              canonical K-major SWIZZLE_128B layout (x = hi + lo to 16 mantissa bits); NC = 8, or 16 when
+//                              the prologue evaluates a swish per element (the elementwise work of the whole SM sits in
+//                              these warps: with 4 of them the kernel was converter-latency-bound at 0.1-0.2 of the roofline)
 //   warp 1      MMA issuer   : 3 x tcgen05.mma kind::f16 per K16 (lo*hi, hi*lo, hi*hi), fp32 accumulation in TMEM;
 //                              two accumulators (2 x 128 columns) so unit u+1 accumulates while unit u drains
-//   warps 6-9   epilogue     : tcgen05.ld -> bias / BN affine / drop-connect / residual -> either 128-byte-row swizzled
+//   4 warps     epilogue     : tcgen05.ld -> bias / BN affine / drop-connect / residual -> either 128-byte-row swizzled
 //                              staging + TMA tile store (plain outputs: every store is a full line), or direct stores
 //                              (small Cout with residual / raw-output save)
 //
@@ -26,7 +28,7 @@
 
 namespace effdet {
 
-constexpr int kPwThreads = 320;
+constexpr int kPwMaxOut = 6;               // staging buffers of the TMA-store epilogue (stores in flight per SM)
 constexpr int kPwA32Half = 128 * 128;      // bytes of one fp32 half-box: 128 rows x 32 floats
 constexpr int kPwA16 = 2 * 128 * 128;      // bytes of one bf16 stage: hi plane + lo plane, 128 rows x 64 bf16 each
 constexpr int kPwOut = 128 * 128;          // bytes of one staging buffer: 128 rows x 32 floats
@@ -44,6 +46,10 @@ struct PwParams {
     int NS;          // ring stages
     int a32_halves;  // fp32 half-boxes per stage (1 when Cin <= 32)
     int tma_store;   // epilogue through shared memory + TMA tile stores
+    int nout;        // staging buffers (tma_store only)
+    int planes;      // the A operand arrives pre-split as bf16 hi/lo planes [2][M][Cin]: TMA writes the MMA operand
+                     // layout directly, no converter work (data gradients of the expand convs: the fused depthwise
+                     // backward emits dz0 in this form for this kernel and for the weight gradient)
 };
 
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
@@ -54,19 +60,26 @@ __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
     lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
 }
 
-__global__ void __launch_bounds__(kPwThreads, 1)
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_upto(int pending) {       // run-time "at most `pending` groups still reading"
+    if (pending >= N) tma_store_wait_read<N>();
+    else if constexpr (N > 0) tma_store_wait_read_upto<N - 1>(pending);
+}
+
+template <int NC>
+__global__ void __launch_bounds__((NC + 6) * 32, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ PwParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const effdet_conv_args& p = P.a;
-    const int a32_bytes = P.a32_halves * kPwA32Half;
+    const int a32_bytes = P.planes ? kPwA16 : P.a32_halves * kPwA32Half;
     const int b_plane = P.BN * 128;
     const int stage_bytes = a32_bytes + 2 * b_plane;
     uint8_t* ring = smem;
     uint8_t* a16 = ring + P.NS * stage_bytes;
-    uint8_t* outst = a16 + 2 * kPwA16;
-    uint64_t* ld_full = reinterpret_cast<uint64_t*>(outst + 2 * kPwOut);
+    uint8_t* outst = a16 + (P.planes ? 0 : 2 * kPwA16);
+    uint64_t* ld_full = reinterpret_cast<uint64_t*>(outst + P.nout * kPwOut);
     uint64_t* ld_empty = ld_full + kPwMaxStages;
     uint64_t* a16_full = ld_empty + kPwMaxStages;
     uint64_t* a16_empty = a16_full + 2;
@@ -79,10 +92,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPwMaxStages; ++s) {
             mbar_init(&ld_full[s], 1);
-            mbar_init(&ld_empty[s], 5);        // 4 converter warps + the MMA commit
+            mbar_init(&ld_empty[s], P.planes ? 1 : NC + 1);   // the converter warps + the MMA commit
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&a16_full[s], 4);
+            mbar_init(&a16_full[s], NC);
             mbar_init(&a16_empty[s], 1);
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 4);
@@ -110,10 +123,16 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint32_t ph = (it / P.NS) & 1;
                     mbar_wait(&ld_empty[s], ph ^ 1);
                     uint8_t* st = ring + s * stage_bytes;
-                    const int halves = (p.Cin - kb * 64 > 32) ? 2 : 1;
-                    mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(halves * kPwA32Half + 2 * b_plane));
-                    tma_load_2d(st, &map_a, &ld_full[s], kb * 64, m0);
-                    if (halves == 2) tma_load_2d(st + kPwA32Half, &map_a, &ld_full[s], kb * 64 + 32, m0);
+                    if (P.planes) {
+                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(kPwA16 + 2 * b_plane));
+                        tma_load_3d(st, &map_a, &ld_full[s], kb * 64, m0, 0);
+                        tma_load_3d(st + kPwA16 / 2, &map_a, &ld_full[s], kb * 64, m0, 1);
+                    } else {
+                        const int halves = (p.Cin - kb * 64 > 32) ? 2 : 1;
+                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(halves * kPwA32Half + 2 * b_plane));
+                        tma_load_2d(st, &map_a, &ld_full[s], kb * 64, m0);
+                        if (halves == 2) tma_load_2d(st + kPwA32Half, &map_a, &ld_full[s], kb * 64 + 32, m0);
+                    }
                     tma_load_3d(st + a32_bytes, &map_b, &ld_full[s], kb * 64, n0, 0);
                     tma_load_3d(st + a32_bytes + b_plane, &map_b, &ld_full[s], kb * 64, n0, 1);
                 }
@@ -133,12 +152,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int s = it % P.NS;
                     const uint32_t ph = (it / P.NS) & 1;
                     const uint32_t sa = it & 1, pha = (it >> 1) & 1;
-                    mbar_wait(&ld_full[s], ph);                // weight tile landed
-                    mbar_wait(&a16_full[sa], pha);             // converters published the bf16 planes
+                    mbar_wait(&ld_full[s], ph);                // weight tile (and, in planes mode, the A planes) landed
+                    if (!P.planes) mbar_wait(&a16_full[sa], pha);      // converters published the bf16 planes
                     tc_fence_after();
                     const int valid = p.Cin - kb * 64;
                     const int ksteps = valid >= 64 ? 4 : (valid + 15) >> 4;
-                    const uint32_t a_hi = smem_u32(a16 + sa * kPwA16), a_lo = a_hi + kPwA16 / 2;
+                    const uint32_t a_hi = P.planes ? smem_u32(ring + s * stage_bytes) : smem_u32(a16 + sa * kPwA16);
+                    const uint32_t a_lo = a_hi + kPwA16 / 2;
                     const uint32_t b_hi = smem_u32(ring + s * stage_bytes + a32_bytes), b_lo = b_hi + b_plane;
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
@@ -147,21 +167,24 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         umma_bf16(d, dah, dbl, idesc, 1);
                         umma_bf16(d, dah, dbh, idesc, 1);
                     }
-                    umma_commit(&a16_empty[sa]);
+                    if (!P.planes) umma_commit(&a16_empty[sa]);
                     umma_commit(&ld_empty[s]);
                 }
                 umma_commit(&acc_full[acc]);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + NC) {
         // ------------------------------------------------ converters ------------------------------------------------
+        constexpr int RP = 4 * NC;                             // rows per pass (8 threads per row)
         const int tid = threadIdx.x - 64;
         const int j = tid & 7, rbase = tid >> 3;
         const bool pro = p.in_scale != nullptr || p.a_scale != nullptr;
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+        for (int u = blockIdx.x; u < (P.planes ? 0 : P.units); u += gridDim.x) {      // planes mode: nothing to convert
             const int mt = u / P.ntn;
             const int m0 = mt * 128;
+            const int b_first = m0 / P.HW;
+            const bool one_image = (min(m0 + 127, P.M - 1) / P.HW) == b_first;   // the usual case: HW >> 128
             for (int kb = 0; kb < P.KB; ++kb, ++it) {
                 const int s = it % P.NS;
                 const uint32_t ph = (it / P.NS) & 1;
@@ -176,24 +199,27 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int h = 0; h < nh; ++h) {
                     const int c = kb * 64 + h * 32 + 4 * j;
                     const bool col_ok = c < p.Cin;
-                    float4 isc = make_float4(1.f, 1.f, 1.f, 1.f), ish = f4zero();
+                    float4 isc = make_float4(1.f, 1.f, 1.f, 1.f), ish = f4zero(), gate = isc;
                     if (p.in_scale && col_ok) { isc = ldg4(p.in_scale + c); ish = ldg4(p.in_shift + c); }
+                    if (p.a_scale && col_ok && one_image) gate = ldg4(p.a_scale + (long long)b_first * p.Cin + c);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rbase + 16 * i;
+                    for (int i = 0; i < 128 / RP; ++i) {
+                        const int r = rbase + RP * i;
                         float4 v = *reinterpret_cast<const float4*>(a32 + h * kPwA32Half + r * 128 + ((j ^ (r & 7)) << 4));
                         if (pro) {
                             if (!col_ok) {
-                                v = f4zero();
+                                v = f4zero();                  // the swish of a zero-filled column would not be zero
                             } else {
                                 if (p.in_scale) {
                                     const float4 q = f4fma(v, isc, ish);
-                                    v = make_float4(swishf_(q.x), swishf_(q.y), swishf_(q.z), swishf_(q.w));
+                                    v = make_float4(fswish(q.x), fswish(q.y), fswish(q.z), fswish(q.w));
                                 }
                                 if (p.a_scale) {
-                                    const int m = m0 + r;
-                                    const int bi = (m < P.M ? m : P.M - 1) / P.HW;
-                                    v = f4mul(v, ldg4(p.a_scale + (long long)bi * p.Cin + c));
+                                    if (!one_image) {
+                                        const int m = m0 + r;
+                                        gate = ldg4(p.a_scale + (long long)((m < P.M ? m : P.M - 1) / P.HW) * p.Cin + c);
+                                    }
+                                    v = f4mul(v, gate);
                                 }
                             }
                         }
@@ -214,7 +240,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
     } else {
         // ------------------------------------------------ epilogue --------------------------------------------------
-        const int etid = threadIdx.x - 192;
+        const int etid = threadIdx.x - (2 + NC) * 32;
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
         const int r = quarter * 32 + lane;                     // row of the tile owned by this thread
         uint32_t iu = 0, nstore = 0;
@@ -255,8 +281,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (lane == 0) mbar_arrive(&acc_empty[acc]);
                 }
                 if (P.tma_store) {
-                    uint8_t* buf = outst + (nstore & 1) * kPwOut;
-                    if (etid == 0) tma_store_wait_read<1>();   // the store that last used this buffer has read it
+                    uint8_t* buf = outst + (nstore % P.nout) * kPwOut;
+                    if (etid == 0) tma_store_wait_read_upto<kPwMaxOut - 1>(P.nout - 1);   // the store that last used this buffer has read it
                     named_bar_sync(1, 128);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -323,6 +349,7 @@ static bool pw_enabled() {
 bool pw_gemm_eligible(const effdet_conv_args* a) {
     if (!pw_enabled() || a->ksize != 1 || a->w_tc == nullptr || a->Cin % 4 || a->Cout % 4 || a->Cin < 8 || a->Cout < 8) return false;
     const long long HW = (long long)a->H * a->W;
+    if (a->x_planes) return a->Cin % 8 == 0 && !a->in_scale && !a->a_scale && (long long)a->B * HW < (1ll << 31);
     if (a->x_bstride != HW * a->Cin) return false;              // x must be one dense [M, Cin] matrix for the 2-D tensor map
     if ((long long)a->B * HW >= (1ll << 31)) return false;
     return true;
@@ -344,20 +371,45 @@ int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st) {
     const int mtiles = cdiv(P.M, 128);
     P.units = mtiles * P.ntn;
     P.a32_halves = a->Cin > 32 ? 2 : 1;
+    P.planes = a->x_planes ? 1 : 0;
     P.tma_store = (!a->z && !a->scale && !a->row_scale && !a->residual && !a->mask_src && a->act == EFFDET_ACT_NONE &&
                    a->y_bstride == (long long)P.HW * a->Cout)
                       ? 1
                       : 0;
-    const int stage_bytes = P.a32_halves * kPwA32Half + P.BN * 256;
-    const int fixed = 2 * kPwA16 + 2 * kPwOut + kPwBarBytes + kPwChanBytes + 1024;
-    int ns = (227 * 1024 - fixed) / stage_bytes;
+    const int stage_bytes = (P.planes ? kPwA16 : P.a32_halves * kPwA32Half) + P.BN * 256;
+    const int fixed = (P.planes ? 0 : 2 * kPwA16) + kPwBarBytes + kPwChanBytes + 1024;
+    const int budget = 227 * 1024 - fixed;
+    // shared memory split: loads in flight (ring stages) vs stores in flight (staging buffers of the TMA-store epilogue)
+    int ns, nout = 0;
+    if (P.tma_store) {
+        nout = 4;
+        ns = (budget - nout * kPwOut) / stage_bytes;
+        if (ns < 2) { nout = 2; ns = (budget - nout * kPwOut) / stage_bytes; }
+        if (ns >= 2) {                                              // left-over space -> more staging buffers
+            if (ns > 3) ns = 3;
+            nout = (budget - ns * stage_bytes) / kPwOut;
+            if (nout > kPwMaxOut) nout = kPwMaxOut;
+        }
+    } else {
+        ns = budget / stage_bytes;
+    }
     if (ns > kPwMaxStages) ns = kPwMaxStages;
     if (ns < 2) return fail(EFFDET_ERR_UNSUPPORTED, "conv2d(pw): shared memory budget");
     P.NS = ns;
-    const size_t smem = (size_t)fixed + (size_t)ns * stage_bytes;
+    P.nout = nout;
+    const size_t smem = (size_t)fixed + (size_t)ns * stage_bytes + (size_t)nout * kPwOut;
 
     CUtensorMap map_a, map_b, map_y;
-    {
+    if (P.planes) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)a->Cin, (cuuint64_t)P.M, 2};
+        const cuuint64_t gstr[2] = {(cuuint64_t)a->Cin * 2, (cuuint64_t)P.M * a->Cin * 2};
+        const cuuint32_t box[3] = {64, 128, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->x_planes), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv2d(pw): tensor map of the x planes failed (%d)", (int)r);
+    } else {
         const cuuint64_t gdim[2] = {(cuuint64_t)a->Cin, (cuuint64_t)P.M};
         const cuuint64_t gstr[1] = {(cuuint64_t)a->Cin * 4};
         const cuuint32_t box[2] = {32, 128};
@@ -388,10 +440,17 @@ int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st) {
     } else {
         map_y = map_a;
     }
-    cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(pw): smem opt-in: %s", cudaGetErrorString(e));
     const int grid = P.units < 148 ? P.units : 148;
-    pw_gemm_kernel<<<grid, kPwThreads, smem, st>>>(map_a, map_b, map_y, P);
+    cudaError_t e;
+    if (a->in_scale) {          // a swish per staged element: 16 converter warps
+        e = cudaFuncSetAttribute(pw_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(pw): smem opt-in: %s", cudaGetErrorString(e));
+        pw_gemm_kernel<16><<<grid, (16 + 6) * 32, smem, st>>>(map_a, map_b, map_y, P);
+    } else {
+        e = cudaFuncSetAttribute(pw_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d(pw): smem opt-in: %s", cudaGetErrorString(e));
+        pw_gemm_kernel<8><<<grid, (8 + 6) * 32, smem, st>>>(map_a, map_b, map_y, P);
+    }
     return launch_status("pw_gemm_kernel");
 }
 

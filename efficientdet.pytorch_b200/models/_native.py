@@ -76,13 +76,13 @@ class ConvArgs(ctypes.Structure):
                 ('bias', _P), ('scale', _P), ('shift', _P), ('a_scale', _P), ('row_scale', _P),
                 ('residual', _P), ('r_bstride', _I64), ('mask_src', _P), ('m_bstride', _I64),
                 ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32),
-                ('w_tc', _P), ('in_scale', _P), ('in_shift', _P)]
+                ('w_tc', _P), ('in_scale', _P), ('in_shift', _P), ('x_planes', _P)]
 
 
 class WgradArgs(ctypes.Structure):
     _fields_ = [('x', _P), ('x_bstride', _I64), ('dy', _P), ('dy_bstride', _I64), ('dw', _P), ('dbias', _P),
                 ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32),
-                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P), ('in_scale', _P), ('in_shift', _P)]
+                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P), ('in_scale', _P), ('in_shift', _P), ('dy_planes', _P)]
 
 
 class BnActBwdArgs(ctypes.Structure):
@@ -102,7 +102,7 @@ class DwBwdArgs(ctypes.Structure):
                 ('rstd1', _P), ('x', _P), ('scale0', _P), ('shift0', _P), ('mean0', _P), ('rstd0', _P), ('w_kkc', _P),
                 ('dx', _P), ('dw', _P), ('dgamma1', _P), ('dbeta1', _P), ('dgamma0', _P), ('dbeta0', _P),
                 ('inv_hw', _F), ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('k', _I32), ('stride', _I32),
-                ('pad_t', _I32), ('pad_l', _I32), ('Ho', _I32), ('Wo', _I32)]
+                ('pad_t', _I32), ('pad_l', _I32), ('Ho', _I32), ('Wo', _I32), ('dx_planes', _P)]
 
 
 class FuseArgs(ctypes.Structure):
@@ -157,7 +157,8 @@ SIGNATURES = {
     'effdet_nchw_to_nhwc': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
     'effdet_nhwc_to_nchw': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
 }
-PLAIN = {'effdet_version': (ctypes.c_int, []), 'effdet_conv_tc_kpad': (ctypes.c_int, [ctypes.c_int]), 'effdet_last_error': (ctypes.c_char_p, []),
+PLAIN = {'effdet_version': (ctypes.c_int, []), 'effdet_conv_tc_kpad': (ctypes.c_int, [ctypes.c_int]),
+         'effdet_wgrad_tc_geometry_ok': (ctypes.c_int, [ctypes.c_int] * 3), 'effdet_last_error': (ctypes.c_char_p, []),
          'effdet_launch_count': (ctypes.c_uint64, []), 'effdet_reset_launch_count': (None, [])}
 
 _lib = None

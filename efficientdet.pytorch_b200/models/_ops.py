@@ -180,13 +180,28 @@ def bn_fold(gamma, beta, rmean, rvar, eps):
 
 def conv2d_raw(dev_t, x_ptr, x_bs, wf, y_ptr, y_bs, B, H, W, Cin, Cout, k, z_ptr=None, bias=None, scale=None,
                shift=None, a_scale=None, row_scale=None, res_ptr=None, res_bs=0, mask_ptr=None, mask_bs=0,
-               act=ACT_NONE, w_tc=None, in_scale=None, in_shift=None):
+               act=ACT_NONE, w_tc=None, in_scale=None, in_shift=None, x_planes=None):
     a = N.ConvArgs(x_ptr, x_bs, N.f32(wf, 'packed weight'), y_ptr, y_bs, z_ptr, N.f32(bias, 'bias'),
                    N.f32(scale, 'scale'), N.f32(shift, 'shift'), N.f32(a_scale, 'a_scale'),
                    N.f32(row_scale, 'row_scale'), res_ptr, res_bs, mask_ptr, mask_bs, B, H, W, Cin, Cout, k, act,
                    w_tc.data_ptr() if w_tc is not None else None, N.f32(in_scale, 'in_scale'),
-                   N.f32(in_shift, 'in_shift'))
+                   N.f32(in_shift, 'in_shift'), N.ptr(x_planes))
     N.call('effdet_conv2d', dev_t, a)
+
+
+def split_planes_like(x):
+    """bf16 hi/lo plane buffer [2, B, H, W, C] for an NHWC fp32 tensor shape (x ~= hi + lo, the tensor-core operand form)."""
+    return torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.bfloat16)
+
+
+def conv2d_from_planes(planes, wf, Cout, residual=None, w_tc=None):
+    """1x1 conv whose input exists only as bf16 hi/lo planes [2,B,H,W,Cin] (written by effdet_dwconv_bwd_fused)."""
+    _, B, H, W, Cin = planes.shape
+    y = torch.empty((B, H, W, Cout), device=planes.device, dtype=torch.float32)
+    bs = H * W * Cout
+    conv2d_raw(y, None, H * W * Cin, wf, N.f32(y), bs, B, H, W, Cin, Cout, 1, res_ptr=N.f32(residual, 'residual'), res_bs=bs,
+               w_tc=w_tc, x_planes=planes)
+    return y
 
 
 def conv2d(x, wf, Cout, k, bias=None, scale=None, shift=None, a_scale=None, row_scale=None, residual=None,
@@ -236,17 +251,23 @@ def conv2d_multi(xs, wf, Cout, k, bias=None, act=ACT_NONE, w_tc=None, residuals=
 
 
 def conv_wgrad_raw(dev_t, x_ptr, x_bs, dy_ptr, dy_bs, dw, dbias, B, H, W, Cin, Cout, k, a_scale=None, tc=False,
-                   in_scale=None, in_shift=None):
+                   in_scale=None, in_shift=None, dy_planes=None):
     ws_x = ws_dy = None
     if tc:
         lib = N.load()
         ws_x = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cin),), device=dev_t.device, dtype=torch.bfloat16)
-        ws_dy = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cout),), device=dev_t.device, dtype=torch.bfloat16)
+        if dy_planes is None:
+            ws_dy = torch.empty((2 * B * H * W * lib.effdet_conv_tc_kpad(Cout),), device=dev_t.device, dtype=torch.bfloat16)
     a = N.WgradArgs(x_ptr, x_bs, dy_ptr, dy_bs, N.f32(dw, 'dw'), N.f32(dbias, 'dbias'), N.f32(a_scale, 'a_scale'),
                     B, H, W, Cin, Cout, k, 1 if tc else 0, ws_x.data_ptr() if ws_x is not None else None,
                     ws_dy.data_ptr() if ws_dy is not None else None, N.f32(in_scale, 'in_scale'),
-                    N.f32(in_shift, 'in_shift'))
+                    N.f32(in_shift, 'in_shift'), N.ptr(dy_planes))
     N.call('effdet_conv2d_wgrad', dev_t, a)
+
+
+def planes_ok(B, H, W, C):
+    """can a [B,H,W,C] gradient be handed to the tensor-core weight / data gradients as bf16 hi/lo planes?"""
+    return tc_enabled() and C % 8 == 0 and bool(N.load().effdet_wgrad_tc_geometry_ok(B, H, W))
 
 
 def conv_wgrad_multi(dev_t, levels, dw, dbias, Cin, Cout, k, tc=False):
@@ -439,24 +460,33 @@ class MBConvFn(torch.autograd.Function):
         # BN1+swish backward (SE product rule), depthwise weight + data gradient, BN0+swish backward: one pass
         dWd, dg1, db1 = zb[5], zb[6], zb[7]
         dw_in = t['z0'] if expand else x
-        dxe = _empty((B, H, W, C), x)
         dg0 = db0 = None
         if expand:
             dg0, db0 = zb[9], zb[10]
+        # with an expand conv the gradient of its raw output is consumed only by tensor-core GEMMs (data + weight
+        # gradient): the kernel writes it as bf16 hi/lo planes, the operand format, instead of fp32 + a split pass
+        planes = split_planes_like(dw_in) if expand and planes_ok(B, H, W, C) else None
+        dxe = None if planes is not None else _empty((B, H, W, C), x)
         ba = N.DwBwdArgs(N.f32(dq), N.f32(z1), N.f32(gate), N.f32(dmean), N.f32(t['sc1']), N.f32(t['sh1']),
                          N.f32(t['rm1'], 'mean'), N.f32(t['rs1']), N.f32(dw_in),
                          N.f32(t['sc0']) if expand else None, N.f32(t['sh0']) if expand else None,
                          N.f32(t['rm0'], 'mean') if expand else None, N.f32(t['rs0']) if expand else None,
                          N.f32(t['wkkc']), N.f32(dxe), N.f32(dWd), N.f32(dg1), N.f32(db1), N.f32(dg0), N.f32(db0),
-                         1.0 / (Ho * Wo), B, H, W, C, k, s, cfg['pad_t'], cfg['pad_l'], Ho, Wo)
-        N.call('effdet_dwconv_bwd_fused', x, ba, nbytes=4.0 * (2 * z1.numel() + 2 * dxe.numel()))
+                         1.0 / (Ho * Wo), B, H, W, C, k, s, cfg['pad_t'], cfg['pad_l'], Ho, Wo,
+                         N.ptr(planes))
+        N.call('effdet_dwconv_bwd_fused', x, ba, nbytes=4.0 * (2 * z1.numel() + 2 * dw_in.numel()))
         grads = []
         if expand:
             We = P[0]
             dWe = zb[8]
-            conv_wgrad(x, dxe, dWe, None, 1, tc=tc_enabled())
             _, wed = pack_conv(We)
-            dx = conv2d(dxe, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
+            if planes is not None:
+                conv_wgrad_raw(x, N.f32(x, 'x'), H * W * x.shape[3], None, H * W * C, dWe, None, B, H, W, x.shape[3], C, 1,
+                               tc=True, dy_planes=planes)
+                dx = conv2d_from_planes(planes, wed, x.shape[3], residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
+            else:
+                conv_wgrad(x, dxe, dWe, None, 1, tc=tc_enabled())
+                dx = conv2d(dxe, wed, x.shape[3], 1, residual=dy if cfg['skip'] else None, w_tc=tc_packs(We)[1])
             grads += [dWe, dg0, db0, None, None]
         else:
             dx = add(dxe, dy) if cfg['skip'] else dxe

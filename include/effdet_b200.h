@@ -75,6 +75,9 @@ typedef struct {
                               operand is swish(x*in_scale+in_shift) (eval-BN + swish applied while the tile is
                               staged, so the activated tensor never exists in HBM: MemoryEfficientSwish keeps
                               only the pre-activation too, models/utils.py:31-42); applied before a_scale */
+    const void* x_planes;  /* optional (1x1 convs, tensor-core path): the input PRE-SPLIT into bf16 planes
+                              [2][B*H*W][Cin] (plane 0 = hi, plane 1 = lo, x ~= hi + lo; Cin % 8 == 0), as written by
+                              effdet_dwconv_bwd_fused; x may then be NULL */
 } effdet_conv_args;
 int effdet_conv2d(const effdet_conv_args* a, int device, effdet_stream_t stream);
 /* The same convolution (shared w / w_tc / bias / act, channels, ksize) applied to `nlevels` (<= 8) feature maps of
@@ -99,6 +102,9 @@ typedef struct {
                               NULL -> the gather-producer tensor-core kernel is used instead */
     const float* in_scale; const float* in_shift; /* [Cin] or both NULL: x is a raw conv output, the operand is
                               swish(x*in_scale+in_shift)*a_scale (see effdet_conv_args) */
+    const void* dy_planes; /* optional (precision 1): dy PRE-SPLIT into bf16 planes [2][B*H*W][Cout] (Cout % 8 == 0), as
+                              written by effdet_dwconv_bwd_fused: no split pass over dy, ws_dy unused, dy may be NULL
+                              (dbias must be NULL) */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
 /* Weight gradient of one shared-weight layer accumulated over `nlevels` feature maps in one launch (all levels
@@ -115,6 +121,9 @@ int effdet_pack_conv_weight(const float* w_oihw, float* w_fwd, float* w_dgrad, i
  *   w_dgrad [2][Cin][k*k][kpad(Cout)]   (rotated 180 degrees and transposed), may be NULL
  * kpad(c) = effdet_conv_tc_kpad(c) = c rounded up to a multiple of 64. */
 int effdet_conv_tc_kpad(int channels);
+/* 1 when the TMA-fed tensor-core weight-gradient kernel can tile a [B,H,W,*] map into pixel boxes (required before
+ * handing it pre-split operands, effdet_wgrad_args.dy_planes); no device work */
+int effdet_wgrad_tc_geometry_ok(int B, int H, int W);
 int effdet_pack_conv_weight_tc(const float* w_oihw, void* w_fwd, void* w_dgrad, int Cout, int Cin, int ksize,
                                int device, effdet_stream_t stream);
 
@@ -185,6 +194,9 @@ typedef struct {
     float* dgamma1; float* dbeta1; float* dgamma0; float* dbeta0;   /* [C] += (BN0 ones may be NULL without BN0) */
     float inv_hw;          /* 1/(Ho*Wo) */
     int32_t B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo;
+    void* dx_planes;       /* optional: write dx as bf16 hi/lo planes [2][B*H*W][C] (dx ~= hi + lo) INSTEAD of fp32 dx
+                              (dx may then be NULL): the form the tensor-core data / weight gradients of the expand conv
+                              consume directly (effdet_conv_args.x_planes, effdet_wgrad_args.dy_planes); C % 8 == 0 */
 } effdet_dw_bwd_args;
 int effdet_dwconv_bwd_fused(const effdet_dw_bwd_args* a, int device, effdet_stream_t stream);
 

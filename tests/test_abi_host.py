@@ -154,16 +154,18 @@ def test_anchor_table_is_bit_exact_on_host():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the contract keys."""
+    """`bench.py --impl reference` prints one JSON line with the contract keys: the reference's own modules when
+    baseline/_ref is installed (baseline/install_ref.sh), otherwise the oracle port -- and says which."""
     import json
     import sys
     out = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                          '--warmup', '0'], capture_output=True, text=True, timeout=900)
+                          '--warmup', '0', '--cpu-bs', '1'], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
                 'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
         assert key in line, key
     assert line['impl'] == 'reference' and line['unit'] == 'img/s' and line['value'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    have_ref = os.path.exists(os.path.join(REPO, 'baseline', '_ref', 'models', 'efficientdet.py'))
+    assert line['cpu_baseline']['kind'] == ('reference' if have_ref else 'port') and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0

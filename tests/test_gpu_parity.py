@@ -230,13 +230,21 @@ def test_dwconv_fused_forward_backward(k, s, pre, C, H, W, B):
                      N.f32(sc0) if pre else None, N.f32(sh0) if pre else None, N.f32(mu0) if pre else None,
                      N.f32(rs0) if pre else None, N.f32(wkkc), N.f32(dx), N.f32(dw), N.f32(dgb[0]), N.f32(dgb[1]),
                      N.f32(dgb[2]) if pre else None, N.f32(dgb[3]) if pre else None, 1.0 / (Ho * Wo), B, H, W, C, k, s, pt, pt,
-                     Ho, Wo)
+                     Ho, Wo, None)
     N.call('effdet_dwconv_bwd_fused', xd, ba)
     errs = dict(dx=_rel(_nchw(dx), xr.grad), dw=_rel(dw.cpu(), wr.grad), dg1=_rel(dgb[0].cpu(), gam[1].grad),
                 db1=_rel(dgb[1].cpu(), bet[1].grad))
     if pre:
         errs.update(dg0=_rel(dgb[2].cpu(), gam[0].grad), db0=_rel(dgb[3].cpu(), bet[0].grad))
     assert max(errs.values()) < TOL_EXACT, errs
+    if pre and C % 8 == 0:                                   # same kernel writing dx as bf16 hi/lo planes instead of fp32
+        planes = torch.full((2, B, H, W, C), float('nan'), device=dev, dtype=torch.bfloat16)
+        dw2, dgb2 = torch.zeros_like(dw), torch.zeros_like(dgb)
+        ba.dx, ba.dx_planes, ba.dw = None, planes.data_ptr(), N.f32(dw2)
+        ba.dgamma1, ba.dbeta1, ba.dgamma0, ba.dbeta0 = (N.f32(dgb2[i]) for i in range(4))
+        N.call('effdet_dwconv_bwd_fused', xd, ba)
+        assert _rel((planes[0].float() + planes[1].float()).permute(0, 3, 1, 2).cpu(), xr.grad) < 3e-5
+        assert _rel(dw2.cpu(), wr.grad) < TOL_EXACT
     # gradient w.r.t. the SE gate with the activation recomputed from the raw tensor
     dgate = torch.zeros(B, C, device=dev)
     N.call('effdet_spatial_reduce_act', xd, N.f32(dqd), N.f32(z1), N.f32(sc1), N.f32(sh1), N.f32(dgate), 1.0, B, Ho * Wo, C)
@@ -308,6 +316,36 @@ def test_pointwise_gemm_persistent_kernel(B, H, W, Cin, Cout):
     dy = torch.randn(B, Cout, H, W, generator=g)                               # data gradient = same kernel, transposed pack
     dx = ops.conv2d(_nhwc(dy), wd, Cin, 1, w_tc=td)
     assert _rel(_nchw(dx), F.conv_transpose2d(dy, w)) < TOL_TC
+
+
+@pytest.mark.parametrize('B,H,W,Cin,Cexp', [(2, 32, 32, 16, 96), (1, 64, 64, 24, 144), (2, 16, 16, 80, 480), (3, 8, 8, 192, 1152)])
+def test_expand_gradients_from_bf16_planes(B, H, W, Cin, Cexp):
+    """The gradient of the expand conv's raw output exists only as bf16 hi/lo planes (written by
+    effdet_dwconv_bwd_fused): data gradient (pw_gemm_kernel, planes mode: TMA straight into the MMA operand layout)
+    and weight gradient (TMA-fed kernel, no split pass) from planes vs torch fp32."""
+    ops = _ops()
+    dev = _dev()
+    assert ops.planes_ok(B, H, W, Cexp)
+    g = torch.Generator().manual_seed(B + Cin + Cexp)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cexp, Cin, 1, 1, generator=g) / Cin ** 0.5
+    dz = torch.randn(B, Cexp, H, W, generator=g)
+    res = torch.randn(B, Cin, H, W, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    F.conv2d(xr, wr).backward(dz)
+    dzd = _nhwc(dz)
+    hi = dzd.to(torch.bfloat16)
+    lo = (dzd - hi.float()).to(torch.bfloat16)
+    planes = torch.stack([hi, lo]).contiguous()
+    wp = torch.nn.Parameter(w.to(dev))
+    _, wd = ops.pack_conv(wp)
+    td = ops.tc_packs(wp)[1]
+    dx = ops.conv2d_from_planes(planes, wd, Cin, residual=_nhwc(res), w_tc=td)
+    assert _rel(_nchw(dx), xr.grad + res) < TOL_TC
+    dw = torch.zeros(Cexp, Cin, 1, 1, device=dev)
+    xd = _nhwc(x)
+    ops.conv_wgrad_raw(xd, ops.N.f32(xd), H * W * Cin, None, H * W * Cexp, dw, None, B, H, W, Cin, Cexp, 1, tc=True, dy_planes=planes)
+    assert _rel(dw.cpu(), wr.grad) < TOL_TC
 
 
 def test_layout_transposes():

@@ -90,6 +90,10 @@ class Recorder:
                 px, kk = a['H'] * a['W'], a['ksize'] ** 2
                 assert a['ksize'] in (1, 3) and a['Cin'] % 4 == 0 and a['Cout'] % 4 == 0, a
                 self.need(a['x'], (a['B'] - 1) * a['x_bstride'] + px * a['Cin'], name + ' x')
+                assert (a['x'] is None) == (a['x_planes'] is not None)
+                if a['x_planes'] is not None:             # bf16 hi/lo planes [2][B*H*W][Cin] = B*H*W*Cin floats' worth of bytes
+                    assert a['ksize'] == 1 and a['Cin'] % 8 == 0 and a['in_scale'] is None and a['a_scale'] is None
+                    self.need(a['x_planes'], a['B'] * px * a['Cin'], name + ' x_planes')
                 self.need(a['y'], (a['B'] - 1) * a['y_bstride'] + px * a['Cout'], name + ' y')
                 self.need(a['z'], a['B'] * px * a['Cout'], name + ' z')
                 self.need(a['w'], kk * a['Cin'] * a['Cout'], name + ' w')
@@ -108,11 +112,16 @@ class Recorder:
                 px, kk = a['H'] * a['W'], a['ksize'] ** 2
                 self.need(a['x'], (a['B'] - 1) * a['x_bstride'] + px * a['Cin'], name + ' x')
                 self.need(a['dy'], (a['B'] - 1) * a['dy_bstride'] + px * a['Cout'], name + ' dy')
+                assert (a['dy'] is None) == (a['dy_planes'] is not None)
+                if a['dy_planes'] is not None:
+                    assert a['precision'] == 1 and a['dbias'] is None and a['Cout'] % 8 == 0
+                    self.need(a['dy_planes'], a['B'] * px * a['Cout'], name + ' dy_planes')
                 self.need(a['dw'], kk * a['Cin'] * a['Cout'], name + ' dw')
                 self.need(a['dbias'], a['Cout'], name + ' dbias')
                 self.need(a['a_scale'], a['B'] * a['Cin'], name + ' a_scale')
                 self.need(a['in_scale'], a['Cin'], name + ' in_scale'); self.need(a['in_shift'], a['Cin'], name + ' in_shift')
-                assert (a['ws_x'] is None) == (a['precision'] == 0) and (a['ws_dy'] is None) == (a['precision'] == 0)
+                assert (a['ws_x'] is None) == (a['precision'] == 0)
+                assert (a['ws_dy'] is None) == (a['precision'] == 0 or a['dy_planes'] is not None)
         elif name in ('effdet_dwconv_fwd', 'effdet_dwconv_bwd_data', 'effdet_dwconv_bwd_weight'):
             B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo = snap[-10:]
             # Conv2dStaticSamePadding on even maps == TF-SAME (models/utils.py:126-155)
@@ -152,6 +161,10 @@ class Recorder:
             else:
                 self.need(a['dq'], small, 'dwb dq'); self.need(a['z1'], small, 'dwb z1')
                 self.need(a['x'], big, 'dwb x'); self.need(a['dx'], big, 'dwb dx')
+                assert (a['dx'] is None) == (a['dx_planes'] is not None)
+                if a['dx_planes'] is not None:
+                    assert C % 8 == 0 and a['scale0'] is not None          # only the expand-conv gradient takes this form
+                    self.need(a['dx_planes'], big, 'dwb dx_planes')
                 self.need(a['gate'], B * C, 'dwb gate'); self.need(a['dmean'], B * C, 'dwb dmean')
                 self.need(a['w_kkc'], k * k * C, 'dwb w'); self.need(a['dw'], k * k * C, 'dwb dw')
                 for f in ('scale1', 'shift1', 'mean1', 'rstd1', 'dgamma1', 'dbeta1'):
