@@ -318,6 +318,277 @@ conv_tc_multi_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant of the multi-level kernel (the RetinaHead towers: 95 % of the model's FLOPs).
+// The single-tile kernel above spends ~25 % of a tile's time outside the MMA main loop (TMEM allocation and barrier set-up,
+// pipeline ramp, and above all the epilogue: 128 x 256 fp32 through thread-per-row stores while the tensor pipe idles).
+// Here a CTA owns its SM for the whole launch and walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the roles are
+// decoupled and the accumulator is double-buffered in TMEM (2 x BN columns = all 512 for BN = 256), so the epilogue of
+// tile i drains accumulator i&1 while the MMA warp is already accumulating tile i+1 into the other one:
+//   warps 0-7   im2col gather producers (as above), running ahead into the next tile as stages free up
+//   warp 8      weight TMA            warp 9   MMA issuer
+//   warps 10-13 epilogue: tcgen05.ld -> bias / ReLU / sigmoid / residual / ReLU-mask -> stores
+// ---------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 448;
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ ConvMultiArgs ma, const int kblocks,
+                       const int ntn, const int total_tiles) {
+    using S = FwdSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* chan = reinterpret_cast<float*>(smem + STAGES * S::kStage + 256);   // [BN] bias of the current n-tile
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const effdet_conv_args& p0 = ma.lv[0];
+    const int taps = p0.ksize * p0.ksize, pad = p0.ksize / 2;
+    const int KT = taps * kblocks;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], kFwdProducers + 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (level, first pixel row, first output channel)
+    auto decode = [&](int tile, int& l, int& m0, int& n0) {
+        const int mt = tile / ntn;
+        n0 = (tile - mt * ntn) * BN;
+        l = 0;
+        while (l + 1 < ma.nlevels && mt >= ma.tile_begin[l + 1]) ++l;
+        m0 = (mt - ma.tile_begin[l]) * kTileM;
+    };
+
+    if (warp < 8) {
+        // ---------------- producers ------------------------------------------------------------------------------------
+        const int t = threadIdx.x;
+        const int j = t & 7;
+        uint32_t it = 0;                                   // stage counter, continues across tiles
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int l, m0, n0;
+            decode(tile, l, m0, n0);
+            const effdet_conv_args& p = ma.lv[l];
+            const int M = p.B * p.H * p.W, HW = p.H * p.W;
+            long long base[4];
+            int oyx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = i * 32 + (t >> 3);
+                const int m = m0 + r;
+                if (m < M) {
+                    const int b = m / HW;
+                    const int pix = m - b * HW;
+                    const int oy = pix / p.W;
+                    oyx[i] = (oy << 16) | (pix - oy * p.W);
+                    base[i] = (long long)b * p.x_bstride;
+                } else {
+                    oyx[i] = -1;
+                    base[i] = 0;
+                }
+            }
+            auto load_stage = [&](int kt, float4 (&v)[8]) {
+                const int tap = kt / kblocks;
+                const int c = (kt - tap * kblocks) * kTileK + j * 8;
+                const int ky = tap / p.ksize - pad, kx = tap % p.ksize - pad;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[2 * i] = f4zero();
+                    v[2 * i + 1] = f4zero();
+                    if (oyx[i] >= 0 && c < p.Cin) {
+                        const int iy = (oyx[i] >> 16) + ky, ix = (oyx[i] & 0xffff) + kx;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+                            const float* src = p.x + base[i] + ((long long)iy * p.W + ix) * p.Cin + c;
+                            v[2 * i] = ldg4(src);
+                            if (c + 4 < p.Cin) v[2 * i + 1] = ldg4(src + 4);
+                        }
+                    }
+                }
+            };
+            auto store_stage = [&](int kt, const float4 (&v)[8]) {
+                const uint32_t g = it + kt;
+                const int s = g % STAGES;
+                const uint32_t ph = (g / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_hi = smem + s * S::kStage;
+                uint8_t* a_lo = a_hi + S::kA;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 32 + (t >> 3);
+                    uint4 hi, lo;
+                    split8(v[2 * i], v[2 * i + 1], hi, lo);
+                    const int off = r * 128 + ((j ^ (r & 7)) << 4);
+                    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full_bar[s]);
+            };
+            float4 va[8], vb[8];
+            load_stage(0, va);
+            for (int kt = 0; kt < KT; kt += 2) {
+                if (kt + 1 < KT) load_stage(kt + 1, vb);
+                store_stage(kt, va);
+                if (kt + 1 < KT) {
+                    if (kt + 2 < KT) load_stage(kt + 2, va);
+                    store_stage(kt + 1, vb);
+                }
+            }
+            it += KT;
+        }
+    } else if (warp == 8) {
+        // ---------------- TMA: weight tiles of the tile's n-range (hi plane, lo plane) --------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int l, m0, n0;
+                decode(tile, l, m0, n0);
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* b_hi = smem + s * S::kStage + 2 * S::kA;
+                    mbar_arrive_expect_tx(&full_bar[s], 2 * S::kB);
+                    tma_load_3d(b_hi, &wmap, &full_bar[s], kt * kTileK, n0, 0);
+                    tma_load_3d(b_hi + S::kB, &wmap, &full_bar[s], kt * kTileK, n0, 1);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ---------------- MMA issue -----------------------------------------------------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kTileM, BN, 0, 0);
+            uint32_t it = 0, iu = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iu) {
+                const uint32_t acc = iu & 1, pacc = (iu >> 1) & 1;
+                mbar_wait(&acc_empty[acc], pacc ^ 1);              // the epilogue warps have drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_base + acc * BN;
+                for (int kt = 0; kt < KT; ++kt, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * S::kStage);
+                    const uint32_t a_lo = a_hi + S::kA;
+                    const uint32_t b_hi = a_hi + 2 * S::kA;
+                    const uint32_t b_lo = b_hi + S::kB;
+#pragma unroll
+                    for (int k = 0; k < kTileK / 16; ++k) {
+                        const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
+                        const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024), dbl = umma_desc(b_lo + k * 32, 16, 1024);
+                        umma_bf16(d, dal, dbh, idesc, (kt | k) != 0);
+                        umma_bf16(d, dah, dbl, idesc, 1);
+                        umma_bf16(d, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ---------------- epilogue warps ------------------------------------------------------------------------------------
+        const int etid = threadIdx.x - 320;
+        const int quarter = warp & 3;
+        uint32_t iu = 0;
+        int chan_n0 = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iu) {
+            int l, m0, n0;
+            decode(tile, l, m0, n0);
+            const effdet_conv_args& p = ma.lv[l];
+            const int M = p.B * p.H * p.W, HW = p.H * p.W;
+            if (n0 != chan_n0) {                                   // bias slice of this n-tile (shared by all levels)
+                named_bar_sync(1, 128);
+                for (int i = etid; i < BN; i += 128) chan[i] = (n0 + i < p.Cout && p.bias) ? __ldg(p.bias + n0 + i) : 0.f;
+                named_bar_sync(1, 128);
+                chan_n0 = n0;
+            }
+            const uint32_t acc = iu & 1, pacc = (iu >> 1) & 1;
+            mbar_wait(&acc_full[acc], pacc);
+            tc_fence_after();
+            const int m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < M;
+            int b = 0;
+            long long pix = 0;
+            if (row_ok) {
+                b = m / HW;
+                pix = m - (long long)b * HW;
+            }
+            const int ncols = min(BN, p.Cout - n0);
+            const int nchunks = (ncols + 31) >> 5;
+            const long long ybase = (long long)b * p.y_bstride + pix * p.Cout;
+            const long long rbase = (long long)b * p.r_bstride + pix * p.Cout;
+            const long long mbase = (long long)b * p.m_bstride + pix * p.Cout;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int cc = 0; cc < nchunks; ++cc) {
+                uint32_t a32[32];
+                tmem_ld32_issue(taddr + cc * 32, a32);
+                float4 rv[8], mv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = n0 + cc * 32 + q * 4;
+                    rv[q] = f4zero();
+                    mv[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (row_ok && n < p.Cout) {
+                        if (p.residual) rv[q] = ldg4(p.residual + rbase + n);
+                        if (p.mask_src) mv[q] = ldg4(p.mask_src + mbase + n);
+                    }
+                }
+                tmem_ld32_wait(a32);
+                if (cc == nchunks - 1) {                           // accumulator drained: the MMA warp may reuse it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                }
+                if (!row_ok) continue;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int nl = cc * 32 + q * 4;
+                    const int n = n0 + nl;
+                    if (n >= p.Cout) break;
+                    float4 v = make_float4(__uint_as_float(a32[q * 4]), __uint_as_float(a32[q * 4 + 1]),
+                                           __uint_as_float(a32[q * 4 + 2]), __uint_as_float(a32[q * 4 + 3]));
+                    v = f4add(v, *reinterpret_cast<const float4*>(chan + nl));
+                    if (p.act == EFFDET_ACT_RELU) {
+                        v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+                    } else if (p.act == EFFDET_ACT_SIGMOID) {
+                        v = make_float4(sigmoidf_(v.x), sigmoidf_(v.y), sigmoidf_(v.z), sigmoidf_(v.w));
+                    } else if (p.act == EFFDET_ACT_SWISH) {
+                        v = make_float4(swishf_(v.x), swishf_(v.y), swishf_(v.z), swishf_(v.w));
+                    }
+                    v = f4add(v, rv[q]);
+                    if (p.mask_src)
+                        v = make_float4(mv[q].x > 0.f ? v.x : 0.f, mv[q].y > 0.f ? v.y : 0.f, mv[q].z > 0.f ? v.z : 0.f,
+                                        mv[q].w > 0.f ? v.w : 0.f);
+                    st4(p.y + ybase + n, v);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<2 * BN>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight-gradient kernel:  D[n, c | tap] += sum_pixels dy[pixel, n] * x[pixel + tap, c]
 //   GEMM-M = 128 output channels, GEMM-N = BC input channels, GEMM-K = pixels (64 per stage);
 //   both operands are NHWC rows (channels contiguous) = MN-major SWIZZLE_128B operands:
@@ -981,6 +1252,27 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
         tiles += cdiv((long long)levels[l].B * levels[l].H * levels[l].W, kTileM);
     }
     for (int l = nlevels; l <= kMaxLevels; ++l) ma.tile_begin[l] = tiles;
+    static const bool persist = [] {
+        const char* v = getenv("EFFDET_B200_PERSIST");
+        return !(v && v[0] == '0');
+    }();
+    if (persist) {
+        const int ntn = cdiv(a->Cout, BN);
+        const int total = tiles * ntn;
+        const int pgrid = total < 148 ? total : 148;
+#define EFFDET_TCP_LAUNCH(BN_, ST_)                                                                                        \
+    do {                                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             FwdSmem<BN_, ST_>::kBytes);                                                  \
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv2d_multi(tc): smem opt-in: %s", cudaGetErrorString(e)); \
+        conv_tc_persist_kernel<BN_, ST_><<<pgrid, kPersistThreads, FwdSmem<BN_, ST_>::kBytes, st>>>(map, ma, kblocks, ntn, total); \
+    } while (0)
+        if (BN == 64) EFFDET_TCP_LAUNCH(64, 4);
+        else if (BN == 128) EFFDET_TCP_LAUNCH(128, 3);
+        else EFFDET_TCP_LAUNCH(256, 2);
+#undef EFFDET_TCP_LAUNCH
+        return launch_status("conv_tc_persist_kernel");
+    }
     dim3 grid(tiles, cdiv(a->Cout, BN));
 #define EFFDET_TCM_LAUNCH(BN_, ST_)                                                                                        \
     do {                                                                                                                  \

@@ -120,6 +120,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, double th
     const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
     const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
     const float width = fmaxf(__fsub_rn(right, left), 0.f), height = fmaxf(__fsub_rn(bottom, top), 0.f);
+    // disjoint boxes (the overwhelming majority of pairs): inter == 0 -> IoU is 0 (or 0/0 = NaN): never > thr for thr >= 0,
+    // so the exact division below is skipped; the result is unchanged
+    if ((width <= 0.f || height <= 0.f) && thr >= 0.0) return false;
     const float inter = __fmul_rn(width, height);
     const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
     const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -147,22 +150,51 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
     mask[(long long)i * col_blocks + cb] = bits;
 }
 
-// sequential greedy scan over the sorted candidates, one CTA; `removed` bitmap lives in smem
+// Greedy scan over the sorted candidates, one CTA; the `removed` bitmap lives in shared memory.  Candidates are
+// consumed 64 at a time: warp 0 resolves the block's internal dependencies from the 64 diagonal mask words (a
+// sequential walk over 64 bits, registers + shuffles only), then every thread ORs the rows of the block's survivors
+// into its slice of `removed`.  Two CTA barriers per 64 candidates instead of two per kept box: the scan used to be
+// 255 ms for the 55 k survivors of a random-weight D7 image.  Result identical to the one-at-a-time scan.
 __global__ void __launch_bounds__(1024) nms_scan_kernel(const uint64_t* __restrict__ mask, const uint64_t* __restrict__ keys,
                                                         int n, int32_t* __restrict__ keep_idx, int32_t* __restrict__ nkeep) {
     extern __shared__ uint64_t removed[];
+    __shared__ uint64_t keep_bits;
     const int col_blocks = (n + 63) / 64;
+    const int lane = threadIdx.x & 31;
     for (int j = threadIdx.x; j < col_blocks; j += blockDim.x) removed[j] = 0;
     __syncthreads();
     int kept = 0;
-    for (int i = 0; i < n; ++i) {
-        const int nb = i >> 6;
-        if ((removed[nb] >> (i & 63)) & 1ull) continue;   // uniform across the CTA
-        if (threadIdx.x == 0) keep_idx[kept] = (int32_t)(uint32_t)keys[i];
-        ++kept;
-        __syncthreads();   // everyone has read removed[nb] before it is modified
-        const uint64_t* row = mask + (long long)i * col_blocks;
-        for (int j = nb + threadIdx.x; j < col_blocks; j += blockDim.x) removed[j] |= row[j];
+    for (int nb = 0; nb < col_blocks; ++nb) {
+        if (threadIdx.x < 32) {
+            const int i0 = nb * 64 + lane, i1 = i0 + 32;
+            const uint64_t d0 = i0 < n ? mask[(long long)i0 * col_blocks + nb] : 0ull;     // bits j > i inside the block
+            const uint64_t d1 = i1 < n ? mask[(long long)i1 * col_blocks + nb] : 0ull;
+            uint64_t rem = removed[nb], kb = 0;
+            const int valid = min(64, n - nb * 64);
+#pragma unroll 1
+            for (int b = 0; b < valid; ++b) {
+                const uint64_t row = __shfl_sync(0xffffffffu, b < 32 ? d0 : d1, b & 31);
+                if (!((rem >> b) & 1ull)) {
+                    kb |= 1ull << b;
+                    rem |= row;
+                }
+            }
+            if (lane == 0) keep_bits = kb;
+        }
+        __syncthreads();
+        const uint64_t kb = keep_bits;
+        if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull))
+            keep_idx[kept + __popcll(kb & ((1ull << threadIdx.x) - 1ull))] = (int32_t)(uint32_t)keys[nb * 64 + threadIdx.x];
+        for (int j = nb + 1 + threadIdx.x; j < col_blocks; j += blockDim.x) {
+            uint64_t acc = 0, bits = kb;
+            while (bits) {
+                const int b = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                acc |= mask[(long long)(nb * 64 + b) * col_blocks + j];
+            }
+            removed[j] |= acc;
+        }
+        kept += __popcll(kb);
         __syncthreads();
     }
     if (threadIdx.x == 0) nkeep[0] = kept;

@@ -47,6 +47,8 @@ struct PwParams {
     int a32_halves;  // fp32 half-boxes per stage (1 when Cin <= 32)
     int tma_store;   // epilogue through shared memory + TMA tile stores
     int nout;        // staging buffers (tma_store only)
+    int bres;        // the whole packed weight (ntn x KB tiles) stays resident in shared memory: loaded once per CTA, the
+                     // ring then carries activations only and is deeper (more loads in flight per SM)
     int planes;      // the A operand arrives pre-split as bf16 hi/lo planes [2][M][Cin]: TMA writes the MMA operand
                      // layout directly, no converter work (data gradients of the expand convs: the fused depthwise
                      // backward emits dz0 in this form for this kernel and for the weight gradient)
@@ -75,9 +77,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const effdet_conv_args& p = P.a;
     const int a32_bytes = P.planes ? kPwA16 : P.a32_halves * kPwA32Half;
     const int b_plane = P.BN * 128;
-    const int stage_bytes = a32_bytes + 2 * b_plane;
+    const int stage_bytes = a32_bytes + (P.bres ? 0 : 2 * b_plane);
     uint8_t* ring = smem;
-    uint8_t* a16 = ring + P.NS * stage_bytes;
+    uint8_t* bres = ring + P.NS * stage_bytes;                         // [ntn][KB][hi | lo] weight tiles (resident mode)
+    uint8_t* a16 = bres + (P.bres ? P.ntn * P.KB * 2 * b_plane : 0);
     uint8_t* outst = a16 + (P.planes ? 0 : 2 * kPwA16);
     uint64_t* ld_full = reinterpret_cast<uint64_t*>(outst + P.nout * kPwOut);
     uint64_t* ld_empty = ld_full + kPwMaxStages;
@@ -85,7 +88,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* a16_empty = a16_full + 2;
     uint64_t* acc_full = a16_empty + 2;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* b_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
     float* chan = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ld_full) + kPwBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,6 +104,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 4);
         }
+        mbar_init(b_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
@@ -114,6 +119,16 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0) {
         // ------------------------------------------------ TMA producer ----------------------------------------------
         if (lane == 0) {
+            const uint32_t btx = P.bres ? 0u : (uint32_t)(2 * b_plane);
+            if (P.bres) {                                          // all weight tiles once, on their own barrier
+                mbar_arrive_expect_tx(b_full, (uint32_t)(P.ntn * P.KB * 2 * b_plane));
+                for (int nt = 0; nt < P.ntn; ++nt)
+                    for (int kb = 0; kb < P.KB; ++kb) {
+                        uint8_t* bt = bres + (nt * P.KB + kb) * 2 * b_plane;
+                        tma_load_3d(bt, &map_b, b_full, kb * 64, nt * P.BN, 0);
+                        tma_load_3d(bt + b_plane, &map_b, b_full, kb * 64, nt * P.BN, 1);
+                    }
+            }
             uint32_t it = 0;
             for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
                 const int mt = u / P.ntn, nt = u - mt * P.ntn;
@@ -124,17 +139,19 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&ld_empty[s], ph ^ 1);
                     uint8_t* st = ring + s * stage_bytes;
                     if (P.planes) {
-                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(kPwA16 + 2 * b_plane));
+                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)kPwA16 + btx);
                         tma_load_3d(st, &map_a, &ld_full[s], kb * 64, m0, 0);
                         tma_load_3d(st + kPwA16 / 2, &map_a, &ld_full[s], kb * 64, m0, 1);
                     } else {
                         const int halves = (p.Cin - kb * 64 > 32) ? 2 : 1;
-                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(halves * kPwA32Half + 2 * b_plane));
+                        mbar_arrive_expect_tx(&ld_full[s], (uint32_t)(halves * kPwA32Half) + btx);
                         tma_load_2d(st, &map_a, &ld_full[s], kb * 64, m0);
                         if (halves == 2) tma_load_2d(st + kPwA32Half, &map_a, &ld_full[s], kb * 64 + 32, m0);
                     }
-                    tma_load_3d(st + a32_bytes, &map_b, &ld_full[s], kb * 64, n0, 0);
-                    tma_load_3d(st + a32_bytes + b_plane, &map_b, &ld_full[s], kb * 64, n0, 1);
+                    if (!P.bres) {
+                        tma_load_3d(st + a32_bytes, &map_b, &ld_full[s], kb * 64, n0, 0);
+                        tma_load_3d(st + a32_bytes + b_plane, &map_b, &ld_full[s], kb * 64, n0, 1);
+                    }
                 }
             }
         }
@@ -143,7 +160,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(128, P.BN, 0, 0);
             uint32_t it = 0, iu = 0;
+            if (P.bres) mbar_wait(b_full, 0);                       // resident weights landed
             for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++iu) {
+                const int nt_u = u % P.ntn;
                 const uint32_t acc = iu & 1, pacc = (iu >> 1) & 1;
                 mbar_wait(&acc_empty[acc], pacc ^ 1);          // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -159,7 +178,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const int ksteps = valid >= 64 ? 4 : (valid + 15) >> 4;
                     const uint32_t a_hi = P.planes ? smem_u32(ring + s * stage_bytes) : smem_u32(a16 + sa * kPwA16);
                     const uint32_t a_lo = a_hi + kPwA16 / 2;
-                    const uint32_t b_hi = smem_u32(ring + s * stage_bytes + a32_bytes), b_lo = b_hi + b_plane;
+                    const uint32_t b_hi = P.bres ? smem_u32(bres + (nt_u * P.KB + kb) * 2 * b_plane)
+                                                 : smem_u32(ring + s * stage_bytes + a32_bytes);
+                    const uint32_t b_lo = b_hi + b_plane;
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t dah = umma_desc(a_hi + k * 32, 16, 1024), dal = umma_desc(a_lo + k * 32, 16, 1024);
                         const uint64_t dbh = umma_desc(b_hi + k * 32, 16, 1024), dbl = umma_desc(b_lo + k * 32, 16, 1024);
@@ -376,17 +397,20 @@ int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st) {
                    a->y_bstride == (long long)P.HW * a->Cout)
                       ? 1
                       : 0;
-    const int stage_bytes = (P.planes ? kPwA16 : P.a32_halves * kPwA32Half) + P.BN * 256;
-    const int fixed = (P.planes ? 0 : 2 * kPwA16) + kPwBarBytes + kPwChanBytes + 1024;
+    const int a_stage = P.planes ? kPwA16 : P.a32_halves * kPwA32Half;
+    const int b_all = P.ntn * P.KB * P.BN * 256;                        // every weight tile of the layer (hi + lo)
+    P.bres = b_all <= 64 * 1024 ? 1 : 0;
+    const int stage_bytes = a_stage + (P.bres ? 0 : P.BN * 256);
+    const int fixed = (P.planes ? 0 : 2 * kPwA16) + kPwBarBytes + kPwChanBytes + 1024 + (P.bres ? b_all : 0);
     const int budget = 227 * 1024 - fixed;
     // shared memory split: loads in flight (ring stages) vs stores in flight (staging buffers of the TMA-store epilogue)
     int ns, nout = 0;
     if (P.tma_store) {
-        nout = 4;
+        nout = 3;
         ns = (budget - nout * kPwOut) / stage_bytes;
         if (ns < 2) { nout = 2; ns = (budget - nout * kPwOut) / stage_bytes; }
-        if (ns >= 2) {                                              // left-over space -> more staging buffers
-            if (ns > 3) ns = 3;
+        if (ns > 4) {                                               // plenty of room: split the rest between both sides
+            ns = 4;
             nout = (budget - ns * stage_bytes) / kPwOut;
             if (nout > kPwMaxOut) nout = kPwMaxOut;
         }

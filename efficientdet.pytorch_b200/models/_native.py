@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu',
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu', 'pipeline.cu',
            'loss.cu', 'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
@@ -154,6 +154,9 @@ SIGNATURES = {
     'effdet_gather_detections': [_P, _P, _P, _P, _INT, _P, _P, _P] + _TAIL,
     'effdet_multi_sumsq': [_P, _P, _P, _P, _INT, _INT, _P] + _TAIL,
     'effdet_multi_clip_adamw': [_P] * 7 + [_INT, _INT, _P] + [_F] * 8 + [_INT] + _TAIL,
+    'effdet_normalize_pad': [_P, _P, _P, _P, _P, _INT, _INT, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)] + _TAIL,
+    'effdet_collate_annots': [_P, _P, _P, _P, _P, _P, _INT, _INT] + _TAIL,
+    'effdet_eval_select': [_P, _P, _P, _INT, _F, _F, _INT, _INT, _P, _P, _P, _P] + _TAIL,
     'effdet_nchw_to_nhwc': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
     'effdet_nhwc_to_nchw': [_P, _P, _INT, _INT, _INT, _INT] + _TAIL,
 }

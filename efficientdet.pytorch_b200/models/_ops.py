@@ -90,6 +90,14 @@ def _zeros_like_many(tensors):
 _cache = {}   # id(first tensor) -> (weakref to it, {kind: (signature, value)})
 
 
+def invalidate_caches():
+    """Drop every packed weight / folded BatchNorm derived from parameters.  The caches are keyed on
+    (Tensor._version, data_ptr), which in-place writes through `.data` (`w.data.normal_()`, the idiom the reference's
+    own __init__ uses, models/efficientdet.py:47-53; EMA swaps `p.data.copy_()`) do NOT bump: after such an edit call
+    this (EfficientDet.load_state_dict / train / eval / freeze_bn do it for you)."""
+    _cache.clear()
+
+
 def _cached(params, kind, builder):
     key_t = params[0]
     kid = id(key_t)

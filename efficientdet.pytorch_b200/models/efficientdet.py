@@ -71,6 +71,13 @@ class EfficientDet(nn.Module):
         for layer in self.modules():
             if isinstance(layer, nn.BatchNorm2d):
                 layer.eval()
+        _ops.invalidate_caches()
+
+    def train(self, mode=True):
+        """nn.Module.train + a reset of the parameter-derived caches: mode switches are where weight surgery through
+        `.data` (which the version-keyed caches cannot see) is finished."""
+        _ops.invalidate_caches()
+        return super().train(mode)
 
     # -- the two call conventions -----------------------------------------------------------------------------
     def _raw_predictions(self, images):
@@ -96,6 +103,7 @@ class EfficientDet(nn.Module):
         a `module.` prefix that `train.py:235` / `eval.py:374` then cannot load."""
         if len(state_dict) and all(k.startswith('module.') for k in state_dict):
             state_dict = {k[len('module.'):]: v for k, v in state_dict.items()}
+        _ops.invalidate_caches()
         return super().load_state_dict(state_dict, *args, **kwargs)
 
     @torch.no_grad()

@@ -330,6 +330,29 @@ int effdet_multi_clip_adamw(const uint64_t* p_ptrs, const uint64_t* g_ptrs, cons
                             float bias_c2, int write_clipped_grad, int device, effdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * the step BEFORE the hot path, on the device.  Normalizer + Augmenter (horizontal flip) + zero pad
+ * to the common size + collater + `.cuda().float()` (datasets/augmentation.py:69-91,111-150, train.py:105-106), bit-identical
+ * to NumPy: (float32(u8) - mean) / std evaluated in float64, then cast to float32.  cv2.resize is not reproduced: images
+ * enter at their final resolution (h, w <= S).
+ *   pixels  : uint8 HWC images back to back, image b starts at byte offsets[b] and is hw[2b] x hw[2b+1] x 3
+ *   flip    : [B] or NULL;  out_nchw : float32 [B,3,S,S];  mean3 / std3 : 3 host doubles
+ *   annotations: rows [sum n_b, 5] float64, image b owns rows row_off[b] .. row_off[b+1]; out float32 [B,G,5], -1 padded;
+ *   scale [B] float64 or NULL (Resizer's box scale), width [B] = image widths (needed with flip)
+ * ------------------------------------------------------------------------------------------ */
+int effdet_normalize_pad(const uint8_t* pixels, const int64_t* offsets, const int32_t* hw, const uint8_t* flip,
+                         float* out_nchw, int B, int S, const double* mean3, const double* std3, int device,
+                         effdet_stream_t stream);
+int effdet_collate_annots(const double* rows, const int32_t* row_off, const double* scale, const uint8_t* flip,
+                          const int32_t* width, float* out, int B, int G, int device, effdet_stream_t stream);
+/* the step AFTER NMS (eval.py:105-128) for one image: boxes /= scale, score > threshold,
+ * top-max_det by score (ties: lower input index), split per label.  out_dets [max_det,5] (x1,y1,x2,y2,score) grouped by
+ * label ascending and in score order inside a label, out_labels [max_det], class_offsets [num_classes+1] (rows of label c
+ * are class_offsets[c] .. class_offsets[c+1]), count[0] = selected rows. */
+int effdet_eval_select(const float* scores, const int64_t* labels, const float* boxes, int n, float scale,
+                       float score_threshold, int max_det, int num_classes, float* out_dets, int32_t* out_labels,
+                       int32_t* class_offsets, int32_t* count, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Layout plumbing at the module boundary (callers see logical NCHW, kernels are NHWC).
  * ------------------------------------------------------------------------------------------ */
 int effdet_nchw_to_nhwc(const float* x, float* y, int B, int C, int H, int W, int device, effdet_stream_t stream);

@@ -908,3 +908,59 @@ def test_detect_batch_matches_per_image_reference(prec):
     m.threshold = 2.0
     for trip in m.detect_batch(x):
         assert trip[0].numel() == 0 and trip[1].numel() == 0 and tuple(trip[2].shape) == (0, 4)
+
+
+def test_data_edits_are_seen_after_invalidate_caches():
+    """in-place writes through `.data` do not bump Tensor._version, so the packed-weight cache would keep
+    serving the old weights; invalidate_caches() (called by load_state_dict / train / eval / freeze_bn) fixes that."""
+    ops = _ops()
+    from models.module import ConvModule
+    conv = ConvModule(8, 16, 3, padding=1).to(_dev())
+    x = torch.randn(1, 8, 8, 8, device=_dev())
+    y0 = conv(x).clone()
+    conv.conv.weight.data.mul_(2.0)                          # invisible to the version counter
+    assert conv.conv.weight._version == 0
+    ops.invalidate_caches()
+    y1 = conv(x)
+    b = conv.conv.bias.detach().view(1, -1, 1, 1)
+    assert _rel((y1 - b).cpu(), (2.0 * (y0 - b)).cpu()) < 1e-5
+
+
+def test_checkpoint_save_resume_round_trip(tmp_path):
+    """SURVEY.md 8(f) rank 4 (train.py:213-236,279-291): train 2 steps with the fused optimizer, save model + optimizer
+    state the way train.py does under DDP (keys prefixed `module.`), resume in a fresh model / optimizer, take the
+    third step on both: parameters must agree (fp32 atomics order is the only difference)."""
+    from models.fused_optim import FusedClipAdamW
+    cfg = O.make_config('efficientdet-d0', num_classes=20, W_bifpn=64, D_bifpn=2)
+    sd = O.init_state_dict(cfg, seed=9)
+    images, ann = O.synthetic_batch(2, size=128, num_classes=20, seed=10)
+    images, ann = images.to(_dev()), ann.to(_dev())
+
+    def make():
+        m = _build('efficientdet-d0', 20, 64, 2, sd, is_training=True)
+        m.eval()
+        m.is_training = True
+        return m, FusedClipAdamW(m.parameters(), lr=1e-3, max_norm=0.1)
+
+    def step(m, opt):
+        opt.zero_grad()
+        cl, rl = m([images, ann])
+        (cl.mean() + rl.mean()).backward()
+        opt.step()
+
+    a, opt_a = make()
+    step(a, opt_a)
+    step(a, opt_a)
+    path = os.path.join(tmp_path, 'ckpt.pth')
+    torch.save({'state_dict': {'module.' + k: v for k, v in a.state_dict().items()}, 'optimizer': opt_a.state_dict()}, path)
+    ck = torch.load(path, map_location='cpu')
+    b, opt_b = make()
+    b.load_state_dict(ck['state_dict'])
+    opt_b.load_state_dict(ck['optimizer'])
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(pa, pb), k
+    step(a, opt_a)
+    step(b, opt_b)
+    worst = max(_rel(pb, pa) for pa, pb in zip(a.parameters(), b.parameters()))
+    assert worst < 1e-5, worst
+    assert int(opt_b.state[next(iter(b.parameters()))]['step']) == 3
