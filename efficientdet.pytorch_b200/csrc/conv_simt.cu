@@ -432,9 +432,12 @@ int effdet::colsum_launch(const float* x, float* out, long long M, int N, long l
 }
 
 extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(a && a->x && (a->dy || a->dy_planes) && a->dw, "wgrad: null tensor");
-    EFFDET_REQUIRE(!a->dy_planes || (a->precision == 1 && !a->dbias && a->Cout % 8 == 0 && aligned16(a->dy_planes) && a->ws_x),
-                   "wgrad: dy_planes needs precision 1, no dbias, Cout %% 8 == 0 and the ws_x workspace");
+    EFFDET_REQUIRE(a && (a->x || a->x_planes) && (a->dy || a->dy_planes) && a->dw, "wgrad: null tensor");
+    EFFDET_REQUIRE(!a->dy_planes || (a->precision == 1 && !a->dbias && aligned16(a->dy_planes) && (a->ws_x || a->x_planes)),
+                   "wgrad: dy_planes needs precision 1, no dbias and the ws_x workspace (or x_planes)");
+    EFFDET_REQUIRE(!a->x_planes || (a->precision == 1 && !a->a_scale && !a->in_scale && aligned16(a->x_planes) &&
+                                    (a->ws_dy || a->dy_planes)),
+                   "wgrad: x_planes needs precision 1 and no input prologue");
     EFFDET_REQUIRE(a->ksize == 1 || a->ksize == 3, "wgrad: ksize %d not in {1,3}", a->ksize);
     EFFDET_REQUIRE(a->Cin % 4 == 0 && a->Cout % 4 == 0, "wgrad: channels must be multiples of 4");
     EFFDET_REQUIRE(aligned16(a->x) && aligned16(a->dy) && aligned16(a->a_scale) && aligned16(a->in_scale) && aligned16(a->in_shift),
@@ -452,7 +455,7 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     bool dbias_done = false;
     if (wgrad_tc_eligible(a)) {
         s = wgrad_tc_launch(a, st, &dbias_done);
-    } else if (a->dy_planes) {
+    } else if (a->dy_planes || a->x_planes) {
         return fail(EFFDET_ERR_UNSUPPORTED, "wgrad: dy_planes given but the TMA-fed tensor-core kernel cannot take this shape "
                                             "(check effdet_wgrad_tc_geometry_ok first)");
     } else {

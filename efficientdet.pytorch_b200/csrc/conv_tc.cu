@@ -763,12 +763,6 @@ EncodeTiledFn encode_fn() {
 
 int conv_tc_kpad(int k) { return (k + kTileK - 1) / kTileK * kTileK; }
 
-struct WgGeom {
-    int Wb, Hb, Bb;          // pixel box of one K stage
-    int nbx, nby, nbb;       // boxes per image row / column / batch
-    int kstage;              // pixels per stage
-};
-
 template <int BC, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const effdet_wgrad_args p,
@@ -1223,7 +1217,6 @@ int conv_tc_launch(const effdet_conv_args* a, cudaStream_t st) {
     return launch_status("conv_tc_kernel");
 }
 
-static bool wg_geometry(int B, int H, int W, WgGeom* g);
 
 int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
@@ -1291,11 +1284,11 @@ int conv_tc_multi_launch(const effdet_conv_args* levels, int nlevels, cudaStream
 bool wgrad_tc_eligible(const effdet_wgrad_args* a) {
     if (a->precision != 1 || a->Cin % 4 || a->Cout % 4 || a->Cin < 16 || a->Cout < 16) return false;
     WgGeom g;
-    const bool tma_ok = a->ws_x && (a->ws_dy || a->dy_planes) && wg_geometry(a->B, a->H, a->W, &g);
-    return tma_ok || (!a->a_scale && !a->in_scale && !a->dy_planes);     // the gather-producer fallback has no input prologue
+    const bool tma_ok = (a->ws_x || a->x_planes) && (a->ws_dy || a->dy_planes) && wg_geometry(a->B, a->H, a->W, &g);
+    return tma_ok || (!a->a_scale && !a->in_scale && !a->dy_planes && !a->x_planes);     // the gather-producer fallback has no input prologue
 }
 
-static bool wg_geometry(int B, int H, int W, WgGeom* g) {
+bool wg_geometry(int B, int H, int W, WgGeom* g) {
     const int Wb = W <= 64 ? W : 64;
     if (W % Wb) return false;
     int Hb = 1;
@@ -1312,10 +1305,12 @@ static bool wg_geometry(int B, int H, int W, WgGeom* g) {
     return true;
 }
 
-static int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, int H, int W, int Cpad, const WgGeom& g) {
-    const cuuint64_t gdim[5] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
-    const cuuint64_t gstr[4] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2,
-                                (cuuint64_t)B * H * W * Cpad * 2};
+// 5-D tensor map (channel, x, y, image, plane) over bf16 hi/lo planes [2][B][H][W][pitch]; C = channel extent (<= pitch):
+// channels beyond C and pixels outside the image are zero-filled by the hardware
+int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, int H, int W, int C, int pitch, const WgGeom& g) {
+    const cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+    const cuuint64_t gstr[4] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2,
+                                (cuuint64_t)B * H * W * pitch * 2};
     const cuuint32_t box[5] = {64, (cuuint32_t)g.Wb, (cuuint32_t)g.Hb, (cuuint32_t)g.Bb, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1328,23 +1323,30 @@ static int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, in
 static int wgrad_tc2_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     WgGeom g;
     EncodeTiledFn enc = encode_fn();
-    if (!enc || !a->ws_x || !(a->ws_dy || a->dy_planes) || !wg_geometry(a->B, a->H, a->W, &g)) return 1;
+    if (!enc || !(a->ws_x || a->x_planes) || !(a->ws_dy || a->dy_planes) || !wg_geometry(a->B, a->H, a->W, &g)) return 1;
     const int HW = a->H * a->W;
     const int cin_pad = conv_tc_kpad(a->Cin), cout_pad = conv_tc_kpad(a->Cout);
-    int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad,
-                                                a->in_scale, a->in_shift);
-    int s = launch_status("split_planes_kernel");
-    if (s) return s;
+    int s = EFFDET_OK;
+    if (!a->x_planes) {
+        int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, a->a_scale, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad,
+                                                    a->in_scale, a->in_shift);
+        s = launch_status("split_planes_kernel");
+        if (s) return s;
+    }
     CUtensorMap mdy, mx;
     if (a->dy_planes) {        // dy arrives pre-split (unpadded pitch; TMA zero-fills the channels beyond Cout)
-        if ((s = planes_map(enc, &mdy, const_cast<void*>(a->dy_planes), a->B, a->H, a->W, a->Cout, g))) return s;
+        if ((s = planes_map(enc, &mdy, const_cast<void*>(a->dy_planes), a->B, a->H, a->W, a->Cout, (a->Cout + 7) / 8 * 8, g))) return s;
     } else {
         if ((s = split_dy_launch(a, cout_pad, st))) return s;      // also accumulates the bias gradient
-        if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, g))) return s;
+        if ((s = planes_map(enc, &mdy, a->ws_dy, a->B, a->H, a->W, cout_pad, cout_pad, g))) return s;
     }
-    if ((s = planes_map(enc, &mx, a->ws_x, a->B, a->H, a->W, cin_pad, g))) return s;
+    if (a->x_planes) {
+        if ((s = planes_map(enc, &mx, const_cast<void*>(a->x_planes), a->B, a->H, a->W, a->Cin, (a->Cin + 7) / 8 * 8, g))) return s;
+    } else {
+        if ((s = planes_map(enc, &mx, a->ws_x, a->B, a->H, a->W, cin_pad, cin_pad, g))) return s;
+    }
     const int taps = a->ksize * a->ksize;
     const int BC = a->Cin > 64 ? 256 : 64;
     const int ctiles = cdiv(a->Cin, BC), ntiles = cdiv(a->Cout, kTileM);
@@ -1383,7 +1385,9 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     int chunks = 0;
     for (int l = 0; l < nlevels; ++l) {
         const effdet_wgrad_args* a = &levels[l];
-        if (!a->ws_x || !a->ws_dy || a->dy_planes || a->a_scale || a->in_scale || !wg_geometry(a->B, a->H, a->W, &ma.g[l])) return 1;
+        if (!(a->ws_x || a->x_planes) || !(a->ws_dy || a->dy_planes) || a->a_scale || a->in_scale ||
+            !wg_geometry(a->B, a->H, a->W, &ma.g[l]))
+            return 1;
         ma.chunk_begin[l] = chunks;
         chunks += ma.g[l].nbx * ma.g[l].nby * ma.g[l].nbb;
     }
@@ -1394,14 +1398,26 @@ int wgrad_tc2_multi_launch(const effdet_wgrad_args* levels, int nlevels, cudaStr
     for (int l = 0; l < nlevels; ++l) {
         const effdet_wgrad_args* a = &levels[l];
         const int HW = a->H * a->W;
-        int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, nullptr, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
-        int s = launch_status("split_planes_kernel");
-        if (s) return s;
-        if ((s = split_dy_launch(a, cout_pad, st))) return s;  // also accumulates the bias gradient
-        if ((s = planes_map(enc, &maps.dy[l], a->ws_dy, a->B, a->H, a->W, cout_pad, ma.g[l]))) return s;
-        if ((s = planes_map(enc, &maps.x[l], a->ws_x, a->B, a->H, a->W, cin_pad, ma.g[l]))) return s;
+        int s = EFFDET_OK;
+        if (a->x_planes) {          // operands that already live as planes: no split pass at all
+            if ((s = planes_map(enc, &maps.x[l], const_cast<void*>(a->x_planes), a->B, a->H, a->W, a->Cin, (a->Cin + 7) / 8 * 8, ma.g[l])))
+                return s;
+        } else {
+            int blocks = cdiv((long long)a->B * HW * (cin_pad / 8), 256);
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            split_planes_kernel<<<blocks, 256, 0, st>>>(a->x, a->x_bstride, nullptr, (__nv_bfloat16*)a->ws_x, a->B, HW, a->Cin, cin_pad);
+            s = launch_status("split_planes_kernel");
+            if (s) return s;
+            if ((s = planes_map(enc, &maps.x[l], a->ws_x, a->B, a->H, a->W, cin_pad, cin_pad, ma.g[l]))) return s;
+        }
+        if (a->dy_planes) {
+            if ((s = planes_map(enc, &maps.dy[l], const_cast<void*>(a->dy_planes), a->B, a->H, a->W, a->Cout, (a->Cout + 7) / 8 * 8,
+                                ma.g[l])))
+                return s;
+        } else {
+            if ((s = split_dy_launch(a, cout_pad, st))) return s;  // also accumulates the bias gradient
+            if ((s = planes_map(enc, &maps.dy[l], a->ws_dy, a->B, a->H, a->W, cout_pad, cout_pad, ma.g[l]))) return s;
+        }
     }
     for (int l = nlevels; l < kWgMaxLevels; ++l) { maps.dy[l] = maps.dy[0]; maps.x[l] = maps.x[0]; }
     const int taps = a0->ksize * a0->ksize;
@@ -1482,7 +1498,8 @@ extern "C" int effdet_conv2d_wgrad_multi(const effdet_wgrad_args* levels, int nl
     bool same = true;
     for (int l = 0; l < nlevels; ++l) {
         const effdet_wgrad_args* a = &levels[l];
-        EFFDET_REQUIRE(a->x && a->dy && a->dw, "conv2d_wgrad_multi: null tensor");
+        EFFDET_REQUIRE((a->x || a->x_planes) && (a->dy || a->dy_planes) && a->dw, "conv2d_wgrad_multi: null tensor");
+        EFFDET_REQUIRE(!(a->dy_planes && a->dbias), "conv2d_wgrad_multi: dy_planes excludes dbias (the producer supplies the column sums)");
         same = same && a->dw == levels[0].dw && a->dbias == levels[0].dbias && a->Cin == levels[0].Cin &&
                a->Cout == levels[0].Cout && a->ksize == levels[0].ksize && a->precision == 1 && wgrad_tc_eligible(a);
     }

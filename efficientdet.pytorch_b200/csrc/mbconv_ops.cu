@@ -1,6 +1,6 @@
 // Element-wise / reduction pieces of the MBConv block that are not convolutions:
 //   * backward of swish(BN_eval(z)) with trainable affine (dgamma, dbeta reductions fused)
-//   * squeeze-excite: spatial mean, the two tiny FC layers and their backward
+//   * squeeze-excite: spatial mean / gate-gradient reductions (the two tiny FC layers live in se_ops.cu)
 // Reference: models/efficientnet.py:75-105 (block), :90-94 (SE), models/utils.py:31-47 (swish),
 //            frozen BN models/efficientdet.py:88-92.  All HBM-bound; NHWC float4 row-packed.
 #include "common.cuh"
@@ -121,80 +121,6 @@ __global__ void __launch_bounds__(256) spatial_reduce_kernel(const float* __rest
     }
 }
 
-// one CTA per sample: s_pre = W1*mean + b1 ; gate = sigmoid(W2*swish(s_pre) + b2)
-__global__ void __launch_bounds__(256) se_gate_fwd_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
-                                                          const float* __restrict__ b1, const float* __restrict__ w2,
-                                                          const float* __restrict__ b2, float* __restrict__ s_pre,
-                                                          float* __restrict__ gate, int C, int S) {
-    extern __shared__ float sm[];
-    float* mu = sm;       // [C]
-    float* sw = sm + C;   // [S]
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int c = t; c < C; c += 256) mu[c] = __ldg(mean + (long long)b * C + c);
-    __syncthreads();
-    for (int j = warp; j < S; j += 8) {
-        float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(mu[c], __ldg(w1 + (long long)j * C + c), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float v = acc + __ldg(b1 + j);
-            s_pre[(long long)b * S + j] = v;
-            sw[j] = swishf_(v);
-        }
-    }
-    __syncthreads();
-    for (int c = t; c < C; c += 256) {
-        float acc = __ldg(b2 + c);
-        for (int j = 0; j < S; ++j) acc = fmaf(sw[j], __ldg(w2 + (long long)c * S + j), acc);
-        gate[(long long)b * C + c] = sigmoidf_(acc);
-    }
-}
-
-__global__ void __launch_bounds__(256) se_gate_bwd_kernel(const float* __restrict__ dgate, const float* __restrict__ mean,
-                                                          const float* __restrict__ s_pre, const float* __restrict__ gate,
-                                                          const float* __restrict__ w1, const float* __restrict__ w2,
-                                                          float* __restrict__ dmean, float* __restrict__ dw1,
-                                                          float* __restrict__ db1, float* __restrict__ dw2,
-                                                          float* __restrict__ db2, int C, int S) {
-    extern __shared__ float sm[];
-    float* dp2 = sm;            // [C]
-    float* sw = sm + C;         // [S] swish(s_pre)
-    float* dp1 = sm + C + S;    // [S]
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int j = t; j < S; j += 256) sw[j] = swishf_(__ldg(s_pre + (long long)b * S + j));
-    __syncthreads();
-    for (int c = t; c < C; c += 256) {
-        const float g = __ldg(gate + (long long)b * C + c);
-        const float d = __ldg(dgate + (long long)b * C + c) * g * (1.f - g);
-        dp2[c] = d;
-        atomicAdd(db2 + c, d);
-        for (int j = 0; j < S; ++j) atomicAdd(dw2 + (long long)c * S + j, d * sw[j]);
-    }
-    __syncthreads();
-    for (int j = warp; j < S; j += 8) {
-        float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(dp2[c], __ldg(w2 + (long long)c * S + j), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float d = acc * swish_gradf_(__ldg(s_pre + (long long)b * S + j));
-            dp1[j] = d;
-            atomicAdd(db1 + j, d);
-        }
-    }
-    __syncthreads();
-    for (int c = t; c < C; c += 256) {
-        const float m = __ldg(mean + (long long)b * C + c);
-        float acc = 0.f;
-        for (int j = 0; j < S; ++j) {
-            const float d = dp1[j];
-            acc = fmaf(d, __ldg(w1 + (long long)j * C + c), acc);
-            atomicAdd(dw1 + (long long)j * C + c, d * m);
-        }
-        dmean[(long long)b * C + c] = acc;
-    }
-}
-
-
 // scale = gamma*rstd ; shift = beta - mean*scale ; rstd = 1/sqrt(var+eps)   (frozen BN -> affine)
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                                const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift,
@@ -308,26 +234,4 @@ extern "C" int effdet_spatial_reduce_act(const float* a, const float* z, const f
     row_grid(HW, C / 4, B, &grid, &rpb);
     spatial_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, z, out, alpha, HW, C, rpb, scale, shift);
     return launch_status("spatial_reduce_kernel");
-}
-
-extern "C" int effdet_se_gate_fwd(const float* mean, const float* w1, const float* b1, const float* w2, const float* b2,
-                                  float* s_pre, float* gate, int B, int C, int S, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(mean && w1 && b1 && w2 && b2 && s_pre && gate, "se_gate_fwd: null tensor");
-    EFFDET_REQUIRE(B > 0 && C > 0 && S > 0 && (size_t)(C + S) * 4 <= 48 * 1024, "se_gate_fwd: bad shape C=%d S=%d", C, S);
-    EFFDET_DEVICE(device);
-    se_gate_fwd_kernel<<<B, 256, (size_t)(C + S) * sizeof(float), (cudaStream_t)stream>>>(mean, w1, b1, w2, b2, s_pre,
-                                                                                       gate, C, S);
-    return launch_status("se_gate_fwd_kernel");
-}
-
-extern "C" int effdet_se_gate_bwd(const float* dgate, const float* mean, const float* s_pre, const float* gate,
-                                  const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2,
-                                  float* db2, int B, int C, int S, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(dgate && mean && s_pre && gate && w1 && w2 && dmean && dw1 && db1 && dw2 && db2,
-                   "se_gate_bwd: null tensor");
-    EFFDET_REQUIRE(B > 0 && C > 0 && S > 0 && (size_t)(C + 2 * S) * 4 <= 48 * 1024, "se_gate_bwd: bad shape");
-    EFFDET_DEVICE(device);
-    se_gate_bwd_kernel<<<B, 256, (size_t)(C + 2 * S) * sizeof(float), (cudaStream_t)stream>>>(
-        dgate, mean, s_pre, gate, w1, w2, dmean, dw1, db1, dw2, db2, C, S);
-    return launch_status("se_gate_bwd_kernel");
 }

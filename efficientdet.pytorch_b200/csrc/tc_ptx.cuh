@@ -174,4 +174,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn encode_fn();      // cuTensorMapEncodeTiled through the runtime's driver entry point table (conv_tc.cu)
 int conv_tc_kpad(int k);
 
+// Pixel boxes of the TMA-fed kernels: a [B,H,W,*] map is tiled into boxes of Wb x Hb x Bb = kstage pixels (16..64, a
+// multiple of 16) that one tensor-map load turns into kstage consecutive 128-byte rows of shared memory (conv_tc.cu)
+struct WgGeom {
+    int Wb, Hb, Bb;          // pixel box
+    int nbx, nby, nbb;       // boxes per image row / column / batch
+    int kstage;              // pixels per box
+};
+bool wg_geometry(int B, int H, int W, WgGeom* g);
+int planes_map(EncodeTiledFn enc, CUtensorMap* map, void* base, int B, int H, int W, int C, int pitch, const WgGeom& g);
+
 }  // namespace effdet

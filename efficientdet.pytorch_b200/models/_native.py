@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'bifpn.cu', 'pipeline.cu',
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_planes.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'se_ops.cu', 'bifpn.cu', 'pipeline.cu',
            'loss.cu', 'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
@@ -82,13 +82,20 @@ class ConvArgs(ctypes.Structure):
 class WgradArgs(ctypes.Structure):
     _fields_ = [('x', _P), ('x_bstride', _I64), ('dy', _P), ('dy_bstride', _I64), ('dw', _P), ('dbias', _P),
                 ('a_scale', _P), ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32),
-                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P), ('in_scale', _P), ('in_shift', _P), ('dy_planes', _P)]
+                ('precision', _I32), ('ws_x', _P), ('ws_dy', _P), ('in_scale', _P), ('in_shift', _P), ('dy_planes', _P),
+                ('x_planes', _P)]
 
 
 class BnActBwdArgs(ctypes.Structure):
     _fields_ = [('dy', _P), ('z', _P), ('dz', _P), ('scale', _P), ('shift', _P), ('mean', _P), ('rstd', _P),
                 ('dgamma', _P), ('dbeta', _P), ('row_scale', _P), ('gate', _P), ('dmean', _P), ('inv_hw', _F),
                 ('B', _I32), ('HW', _I32), ('C', _I32), ('act', _I32)]
+
+
+class ConvPlanesArgs(ctypes.Structure):
+    _fields_ = [('x_planes', _P), ('w_tc', _P), ('bias', _P), ('y', _P), ('y_bstride', _I64), ('y_planes', _P),
+                ('mask_planes', _P), ('residual', _P), ('r_bstride', _I64), ('colsum', _P),
+                ('B', _I32), ('H', _I32), ('W', _I32), ('Cin', _I32), ('Cout', _I32), ('ksize', _I32), ('act', _I32)]
 
 
 class DwFwdArgs(ctypes.Structure):
@@ -124,6 +131,8 @@ SIGNATURES = {
     'effdet_conv2d': [ctypes.POINTER(ConvArgs)] + _TAIL,
     'effdet_conv2d_multi': [ctypes.POINTER(ConvArgs), _INT] + _TAIL,
     'effdet_conv2d_wgrad': [ctypes.POINTER(WgradArgs)] + _TAIL,
+    'effdet_conv_planes_multi': [ctypes.POINTER(ConvPlanesArgs), _INT] + _TAIL,
+    'effdet_to_planes': [_P, _I64, _P, _I64, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_conv2d_wgrad_multi': [ctypes.POINTER(WgradArgs), _INT] + _TAIL,
     'effdet_pack_conv_weight': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
     'effdet_pack_conv_weight_tc': [_P, _P, _P, _INT, _INT, _INT] + _TAIL,
@@ -143,7 +152,7 @@ SIGNATURES = {
     'effdet_spatial_reduce': [_P, _P, _P, _F, _INT, _INT, _INT] + _TAIL,
     'effdet_spatial_reduce_act': [_P, _P, _P, _P, _P, _F, _INT, _INT, _INT] + _TAIL,
     'effdet_se_gate_fwd': [_P] * 7 + [_INT] * 3 + _TAIL,
-    'effdet_se_gate_bwd': [_P] * 11 + [_INT] * 3 + _TAIL,
+    'effdet_se_gate_bwd': [_P] * 12 + [_INT] * 3 + _TAIL,
     'effdet_bifpn_fuse_fwd': [ctypes.POINTER(FuseArgs)] + _TAIL,
     'effdet_bifpn_fuse_bwd': [ctypes.POINTER(FuseBwdArgs)] + _TAIL,
     'effdet_focal_loss_fwd': [_P] * 7 + [_INT] * 4 + [_F, _F] + _TAIL,

@@ -462,9 +462,10 @@ class MBConvFn(torch.autograd.Function):
         S = Wr.shape[0]
         dmean = _empty((B, C), x)
         dWr, dbr, dWx, dbx = zb[1], zb[2], zb[3], zb[4]
+        se_ws = _empty((B * (C + S),), x)
         N.call('effdet_se_gate_bwd', x, N.f32(dgate), N.f32(t['mean']), N.f32(t['s_pre']), N.f32(gate),
                N.f32(_contig(Wr.detach())), N.f32(_contig(Wx.detach())), N.f32(dmean), N.f32(dWr), N.f32(dbr),
-               N.f32(dWx), N.f32(dbx), B, C, S)
+               N.f32(dWx), N.f32(dbx), N.f32(se_ws), B, C, S)
         # BN1+swish backward (SE product rule), depthwise weight + data gradient, BN0+swish backward: one pass
         dWd, dg1, db1 = zb[5], zb[6], zb[7]
         dw_in = t['z0'] if expand else x
@@ -764,6 +765,157 @@ class RetinaHeadFn(torch.autograd.Function):
                 else:
                     d = conv2d_multi(d, wd, Cin, 3, w_tc=wdt, residuals=dfeat)
             dfeat = d
+        ctx.keep = None
+        return (None, None, None, None) + tuple(dfeat) + tuple(gP)
+
+
+def _pitch8(c):
+    return (c + 7) // 8 * 8
+
+
+def _planes(B, H, W, C, like):
+    return torch.empty((2, B, H, W, _pitch8(C)), device=like.device, dtype=torch.bfloat16)
+
+
+def to_planes(x_ptr, x_bs, planes, B, HW, C, dev_t, prob_ptr=None, p_bs=0, colsum=None):
+    N.call('effdet_to_planes', dev_t, x_ptr, x_bs, prob_ptr, p_bs, N.ptr(planes), N.f32(colsum, 'colsum'), B, HW, C,
+           nbytes=8.0 * B * HW * C)
+
+
+def conv_planes_multi(dev_t, levels, w_tc, Cin, Cout, k, bias=None, act=ACT_NONE, colsum=None):
+    """One launch over the pyramid levels; levels: dicts with x (planes), B, H, W and y_planes and / or (y_ptr, y_bs),
+    optional mask (planes), res_ptr / res_bs."""
+    nl = len(levels)
+    arr = (N.ConvPlanesArgs * nl)()
+    for i, lv in enumerate(levels):
+        arr[i] = N.ConvPlanesArgs(N.ptr(lv['x']), w_tc.data_ptr(), N.f32(bias, 'bias'), lv.get('y_ptr'), lv.get('y_bs', 0),
+                                  N.ptr(lv.get('y_planes')), N.ptr(lv.get('mask')), lv.get('res_ptr'), lv.get('res_bs', 0),
+                                  N.f32(colsum, 'colsum'), lv['B'], lv['H'], lv['W'], Cin, Cout, k, act)
+    px = sum(lv['B'] * lv['H'] * lv['W'] for lv in levels)
+    N.call('effdet_conv_planes_multi', dev_t, arr, nl, flops=2.0 * px * k * k * Cin * Cout,
+           nbytes=4.0 * (px * (Cin + Cout) + k * k * Cin * Cout))
+
+
+def wgrad_planes_multi(dev_t, levels, dw, Cin, Cout, k):
+    """weight gradient of one shared-weight layer from operands that already live as planes (no split pass);
+    levels: dicts with x (planes), dy (planes), B, H, W."""
+    nl = len(levels)
+    arr = (N.WgradArgs * nl)()
+    for i, lv in enumerate(levels):
+        arr[i] = N.WgradArgs(None, 0, None, 0, N.f32(dw, 'dw'), None, None, lv['B'], lv['H'], lv['W'], Cin, Cout, k, 1, None,
+                             None, None, None, N.ptr(lv['dy']), N.ptr(lv['x']))
+    N.call('effdet_conv2d_wgrad_multi', dev_t, arr, nl)
+
+
+def head_planes_ok(feats, params):
+    """can the RetinaHead run with activations kept as bf16 hi/lo planes (TMA-fed tensor-core path)?"""
+    if not tc_enabled() or os.environ.get('EFFDET_B200_HEAD_PLANES', '1') == '0':
+        return False
+    lib = N.load()
+    for f in feats:
+        B, H, W, C = f.shape
+        if C % 4 or not lib.effdet_wgrad_tc_geometry_ok(B, H, W):
+            return False
+    return all(p.shape[0] % 4 == 0 and p.shape[0] >= 16 for p in params[0::2])
+
+
+class RetinaHeadPlanesFn(torch.autograd.Function):
+    """RetinaHeadFn with every tower activation (and every tower gradient) stored as bf16 hi/lo planes: each conv is ONE
+    TMA-fed tensor-core launch over all levels, data gradients hand the bias gradient of the previous layer over as a
+    by-product of their epilogue, weight gradients read both operands as they lie -- no split pass, no fp32 tower
+    tensors.  Same arguments / results as RetinaHeadFn (models/retinahead.py:109-132)."""
+
+    @staticmethod
+    def forward(ctx, nl, A, K, stacked, *args):
+        feats = [_contig(t) for t in args[:nl]]
+        P = args[nl:]
+        cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
+        wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
+        dev_t = feats[0]
+        B = feats[0].shape[0]
+        Cin = feats[0].shape[3]
+        F = cls_p[0].shape[0]
+        geo = [(f.shape[0], f.shape[1], f.shape[2]) for f in feats]
+        offs, tot = [], 0
+        for f in feats:
+            offs.append(tot)
+            tot += f.shape[1] * f.shape[2] * A
+        cls_all = _empty((B, tot, K), dev_t)
+        reg_all = _empty((B, tot, 4), dev_t)
+        fp = []
+        for f in feats:                                    # the BiFPN features as planes, shared by both towers
+            pl = _planes(f.shape[0], f.shape[1], f.shape[2], Cin, f)
+            to_planes(N.f32(f), f.shape[1] * f.shape[2] * Cin, pl, f.shape[0], f.shape[1] * f.shape[2], Cin, dev_t)
+            fp.append(pl)
+        towers = []
+        for tp in (cls_p, reg_p):
+            acts = [fp]
+            cur, ci = fp, Cin
+            for i in range(stacked):
+                nxt = [_planes(b, h, w, F, dev_t) for (b, h, w) in geo]
+                conv_planes_multi(dev_t, [dict(x=cur[l], y_planes=nxt[l], B=geo[l][0], H=geo[l][1], W=geo[l][2]) for l in range(nl)],
+                                  tc_packs(tp[2 * i])[0], ci, F, 3, bias=tp[2 * i + 1].detach(), act=ACT_RELU)
+                acts.append(nxt)
+                cur, ci = nxt, F
+            towers.append(acts)
+        for (acts, w, bias, out, width, act) in ((towers[0], wc, bc, cls_all, K, ACT_SIGMOID),
+                                                 (towers[1], wr, br, reg_all, 4, ACT_NONE)):
+            levels = [dict(x=acts[stacked][l], y_ptr=N.f32(out) + 4 * offs[l] * width, y_bs=tot * width, B=geo[l][0], H=geo[l][1],
+                           W=geo[l][2]) for l in range(nl)]
+            conv_planes_multi(dev_t, levels, tc_packs(w)[0], F, A * width, 3, bias=bias.detach(), act=act)
+        ctx.meta = (nl, A, K, stacked, offs, tot, geo, Cin, F)
+        ctx.keep = (P, towers, cls_all)
+        return cls_all, reg_all
+
+    @staticmethod
+    def backward(ctx, dcls, dreg):
+        nl, A, K, stacked, offs, tot, geo, Cin, F = ctx.meta
+        if ctx.keep is None:
+            raise RuntimeError('RetinaHeadPlanesFn: backward called twice (activations are released after the first backward)')
+        P, towers, cls_all = ctx.keep
+        cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
+        wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
+        dcls, dreg = _contig(dcls), _contig(dreg)
+        dev_t = dcls
+        gP = _zeros_like_many(P)
+        g_cls, g_reg = gP[:2 * stacked], gP[2 * stacked:4 * stacked]
+        gwc, gbc, gwr, gbr = gP[4 * stacked:4 * stacked + 4]
+        dfeat = None
+        for (acts, tp, tg, wl, gwl, gbl, dsrc, prob, width) in ((towers[0], cls_p, g_cls, wc, gwc, gbc, dcls, cls_all, K),
+                                                               (towers[1], reg_p, g_reg, wr, gwr, gbr, dreg, None, 4)):
+            Co = A * width
+            # gradient w.r.t. the head outputs -> planes (sigmoid backward folded in) + bias gradient of the output conv
+            d = []
+            for l, (b, h, w) in enumerate(geo):
+                pl = _planes(b, h, w, Co, dev_t)
+                to_planes(N.f32(dsrc) + 4 * offs[l] * width, tot * width, pl, b, h * w, Co, dev_t,
+                          prob_ptr=(N.f32(prob) + 4 * offs[l] * width) if prob is not None else None, p_bs=tot * width, colsum=gbl)
+                d.append(pl)
+            top = acts[stacked]
+            wgrad_planes_multi(dev_t, [dict(x=top[l], dy=d[l], B=geo[l][0], H=geo[l][1], W=geo[l][2]) for l in range(nl)],
+                               gwl, F, Co, 3)
+            nxt = [_planes(b, h, w, F, dev_t) for (b, h, w) in geo]
+            conv_planes_multi(dev_t, [dict(x=d[l], y_planes=nxt[l], mask=top[l], B=geo[l][0], H=geo[l][1], W=geo[l][2])
+                                      for l in range(nl)], tc_packs(wl)[1], Co, F, 3, colsum=tg[2 * (stacked - 1) + 1])
+            d = nxt
+            for i in range(stacked - 1, -1, -1):
+                xin = acts[i]
+                ci = Cin if i == 0 else F
+                wgrad_planes_multi(dev_t, [dict(x=xin[l], dy=d[l], B=geo[l][0], H=geo[l][1], W=geo[l][2]) for l in range(nl)],
+                                   tg[2 * i], ci, F, 3)
+                wdt = tc_packs(tp[2 * i])[1]
+                if i > 0:
+                    nxt = [_planes(b, h, w, F, dev_t) for (b, h, w) in geo]
+                    conv_planes_multi(dev_t, [dict(x=d[l], y_planes=nxt[l], mask=xin[l], B=geo[l][0], H=geo[l][1], W=geo[l][2])
+                                              for l in range(nl)], wdt, F, F, 3, colsum=tg[2 * (i - 1) + 1])
+                    d = nxt
+                else:
+                    out = [_empty((b, h, w, Cin), dev_t) for (b, h, w) in geo]
+                    conv_planes_multi(dev_t, [dict(x=d[l], y_ptr=N.f32(out[l]), y_bs=geo[l][1] * geo[l][2] * Cin,
+                                                   res_ptr=N.f32(dfeat[l]) if dfeat is not None else None,
+                                                   res_bs=geo[l][1] * geo[l][2] * Cin, B=geo[l][0], H=geo[l][1], W=geo[l][2])
+                                              for l in range(nl)], wdt, F, Cin, 3)
+                    dfeat = out
         ctx.keep = None
         return (None, None, None, None) + tuple(dfeat) + tuple(gP)
 

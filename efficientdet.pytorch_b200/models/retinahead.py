@@ -66,8 +66,9 @@ class RetinaHead(nn.Module):
 
     def forward_concat_nhwc(self, feats):
         """NHWC feature maps -> (cls [B, sum(HWA), K] probabilities, reg [B, sum(HWA), 4])."""
-        return _ops.RetinaHeadFn.apply(len(feats), self.num_anchors, self.num_classes, self.stacked_convs,
-                                       *feats, *self._params())
+        params = self._params()
+        fn = _ops.RetinaHeadPlanesFn if _ops.head_planes_ok(feats, params) else _ops.RetinaHeadFn
+        return fn.apply(len(feats), self.num_anchors, self.num_classes, self.stacked_convs, *feats, *params)
 
     def forward_concat(self, feats):
         return self.forward_concat_nhwc([_ops.to_nhwc(f, 'RetinaHead input') for f in feats])

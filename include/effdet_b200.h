@@ -102,14 +102,44 @@ typedef struct {
                               NULL -> the gather-producer tensor-core kernel is used instead */
     const float* in_scale; const float* in_shift; /* [Cin] or both NULL: x is a raw conv output, the operand is
                               swish(x*in_scale+in_shift)*a_scale (see effdet_conv_args) */
-    const void* dy_planes; /* optional (precision 1): dy PRE-SPLIT into bf16 planes [2][B*H*W][Cout] (Cout % 8 == 0), as
-                              written by effdet_dwconv_bwd_fused: no split pass over dy, ws_dy unused, dy may be NULL
-                              (dbias must be NULL) */
+    const void* dy_planes; /* optional (precision 1): dy PRE-SPLIT into bf16 planes [2][B*H*W][pitch(Cout)], as written
+                              by effdet_dwconv_bwd_fused / effdet_conv_planes_multi: no split pass over dy, ws_dy unused,
+                              dy may be NULL (dbias must be NULL) */
+    const void* x_planes;  /* optional, likewise for x ([2][B*H*W][pitch(Cin)]; no a_scale / in_scale): ws_x unused */
 } effdet_wgrad_args;
 int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effdet_stream_t stream);
 /* Weight gradient of one shared-weight layer accumulated over `nlevels` feature maps in one launch (all levels
  * must name the same dw / dbias); falls back to one launch per level when a level cannot use the TMA path. */
 int effdet_conv2d_wgrad_multi(const effdet_wgrad_args* levels, int nlevels, int device, effdet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The same dense convolution with activations kept in HBM as bf16 hi/lo PLANES [2][B][H][W][pitch] (x ~= hi + lo, the
+ * tensor-core operand format; pitch = channels rounded up to 8): the RetinaHead towers end to end
+ * (models/retinahead.py:67-132).  The im2col gather is a TMA load (5-D tensor map, tap = coordinate offset, hardware
+ * zero fill = padding), the epilogue writes the next layer's planes (and / or fp32), so no layer re-splits its input and
+ * no weight gradient needs a split pass.  All levels of one call share weights / bias (RetinaHead.forward).
+ *   epilogue: v = acc + bias; v = act(v); v += residual; v = mask > 0 ? v : 0; store planes and / or fp32;
+ *             colsum[n] += sum over pixels of v   (the bias gradient of the layer that produced this layer's input
+ *             gradient -- a data-gradient launch hands it over for free)
+ * Needs effdet_wgrad_tc_geometry_ok(B,H,W) for every level.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* x_planes;                       /* [2][B][H][W][pitch(Cin)] bf16 */
+    const void* w_tc;                           /* effdet_pack_conv_weight_tc pack (forward or data-gradient) */
+    const float* bias;                          /* [Cout] or NULL */
+    float* y;              int64_t y_bstride;   /* fp32 output [B][H*W][Cout] (image stride y_bstride) or NULL */
+    void* y_planes;                             /* planes output [2][B][H][W][pitch(Cout)] or NULL */
+    const void* mask_planes;                    /* ReLU-backward mask source, planes of pitch(Cout), or NULL */
+    const float* residual; int64_t r_bstride;   /* fp32 [B][H*W][Cout] added before the mask, or NULL */
+    float* colsum;                              /* [Cout] += or NULL */
+    int32_t B, H, W, Cin, Cout, ksize, act;
+} effdet_conv_planes_args;
+int effdet_conv_planes_multi(const effdet_conv_planes_args* levels, int nlevels, int device, effdet_stream_t stream);
+/* fp32 [B][HW][C] (image stride x_bstride) -> planes [2][B*HW][pitch(C)]; with prob != NULL the value is first
+ * multiplied by p*(1-p) (sigmoid backward of the classification head, models/retinahead.py:121); with colsum != NULL
+ * the per-channel sums of what was written are accumulated (bias gradient) in the same pass */
+int effdet_to_planes(const float* x, int64_t x_bstride, const float* prob, int64_t p_bstride, void* planes, float* colsum,
+                     int B, int HW, int C, int device, effdet_stream_t stream);
 
 /* OIHW -> [k*k][Cin][Cout] (forward) and, if w_dgrad != NULL, the 180-degree-rotated transpose
  * [k*k][Cout][Cin] that turns the data gradient into the same implicit GEMM. */
@@ -245,7 +275,8 @@ int effdet_se_gate_fwd(const float* mean, const float* w1, const float* b1, cons
                        float* s_pre, float* gate, int B, int C, int S, int device, effdet_stream_t stream);
 int effdet_se_gate_bwd(const float* dgate, const float* mean, const float* s_pre, const float* gate,
                        const float* w1, const float* w2, float* dmean, float* dw1, float* db1, float* dw2,
-                       float* db2, int B, int C, int S, int device, effdet_stream_t stream);
+                       float* db2, float* ws /* B*(C+S) floats of scratch */, int B, int C, int S, int device,
+                       effdet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * BiFPN fast-normalised fusion node input (BiFPNModule.forward, models/bifpn.py:177-201):

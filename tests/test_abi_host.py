@@ -43,7 +43,7 @@ def test_ctypes_struct_layout_matches_header(native, tmp_path):
     pairs = {'effdet_conv_args': native.ConvArgs, 'effdet_wgrad_args': native.WgradArgs,
              'effdet_bnact_bwd_args': native.BnActBwdArgs, 'effdet_fuse_args': native.FuseArgs,
              'effdet_fuse_bwd_args': native.FuseBwdArgs, 'effdet_dw_fwd_args': native.DwFwdArgs,
-             'effdet_dw_bwd_args': native.DwBwdArgs}
+             'effdet_dw_bwd_args': native.DwBwdArgs, 'effdet_conv_planes_args': native.ConvPlanesArgs}
     for extra in ('PwGemmArgs',):
         if hasattr(native, extra):
             pairs['effdet_pw_gemm_args'] = getattr(native, extra)

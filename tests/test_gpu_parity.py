@@ -512,6 +512,39 @@ def test_head_forward_backward(prec):
     print('head', prec, 'worst grad rel err', worst)
 
 
+@pytest.mark.parametrize('B,top', [(4, 32), (3, 64)])
+def test_head_planes_path_forward_backward(B, top):
+    """RetinaHead with the tower activations / gradients kept as bf16 hi/lo planes (conv_planes_kernel: TMA-fed im2col,
+    epilogue writes the next layer's operand; weight gradients straight from the planes; bias gradients from the data
+    gradients' column sums) against the CPU oracle: forward, feature gradients, every parameter gradient."""
+    from models.retinahead import RetinaHead
+    ops = _ops()
+    cfg = O.make_config('efficientdet-d0', 20, 64, 2)
+    sd = O.init_state_dict(cfg, seed=33)
+    m = _load(RetinaHead(num_classes=20, in_channels=64), sd, 'bbox_head.')
+    g = torch.Generator().manual_seed(6)
+    feats = [torch.randn(B, 64, top >> i, top >> i, generator=g) for i in range(5)]
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    fd = [f.to(_dev()).requires_grad_(True) for f in feats]
+    assert ops.head_planes_ok([ops.to_nhwc(f) for f in fd], m._params())          # this test is about the planes path
+    sdg = _grad_sd(sd)
+    cr, rr = O.head_forward(sdg, fr, cfg)
+    cd, rd = m(fd)
+    lr, l = 0, 0
+    for a, b in list(zip(cd, cr)) + list(zip(rd, rr)):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert _rel(a.detach().cpu(), b.detach()) < 2e-4
+        wgt = torch.randn(b.shape, generator=g)
+        lr = lr + (b * wgt).sum()
+        l = l + (a * wgt.to(_dev())).sum()
+    lr.backward()
+    l.backward()
+    errs = [_rel(a.grad.cpu(), b.grad) for a, b in zip(fd, fr)]
+    worst = _compare_param_grads(m, sdg, 'bbox_head.', tol=5e-2)
+    print('head planes path B=%d: feature grad rel errs %s, worst param grad %s' % (B, ['%.1e' % e for e in errs], worst))
+    assert max(errs) < 5e-2
+
+
 @pytest.mark.parametrize('empty_first', [False, True])
 def test_focal_loss_forward_backward(empty_first):
     from models.losses import FocalLoss
@@ -915,11 +948,12 @@ def test_data_edits_are_seen_after_invalidate_caches():
     serving the old weights; invalidate_caches() (called by load_state_dict / train / eval / freeze_bn) fixes that."""
     ops = _ops()
     from models.module import ConvModule
-    conv = ConvModule(8, 16, 3, padding=1).to(_dev())
+    conv = ConvModule(8, 16, 3, padding=1, activation=None).to(_dev())
     x = torch.randn(1, 8, 8, 8, device=_dev())
     y0 = conv(x).clone()
+    v0 = conv.conv.weight._version
     conv.conv.weight.data.mul_(2.0)                          # invisible to the version counter
-    assert conv.conv.weight._version == 0
+    assert conv.conv.weight._version == v0
     ops.invalidate_caches()
     y1 = conv(x)
     b = conv.conv.bias.detach().view(1, -1, 1, 1)

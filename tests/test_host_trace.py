@@ -199,7 +199,8 @@ class Recorder:
                                (s_pre, B * S, 's_pre'), (gate, B * C, 'gate')):
                 self.need(p_, n_, 'se_gate_fwd ' + w_)
         elif name == 'effdet_se_gate_bwd':
-            dgate, mean, s_pre, gate, w1, w2, dmean, dw1, db1, dw2, db2, B, C, S = snap
+            dgate, mean, s_pre, gate, w1, w2, dmean, dw1, db1, dw2, db2, ws, B, C, S = snap
+            self.need(ws, B * (C + S), 'se_gate_bwd ws')
             for p_, n_, w_ in ((dgate, B * C, 'dgate'), (mean, B * C, 'mean'), (s_pre, B * S, 's_pre'), (gate, B * C, 'gate'),
                                (w1, S * C, 'w1'), (w2, C * S, 'w2'), (dmean, B * C, 'dmean'), (dw1, S * C, 'dw1'),
                                (db1, S, 'db1'), (dw2, C * S, 'dw2'), (db2, C, 'db2')):
