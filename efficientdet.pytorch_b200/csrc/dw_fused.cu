@@ -24,20 +24,22 @@
 
 namespace effdet {
 
-constexpr int kDwT = 128;       // threads per CTA
 constexpr int kCVc = 4;         // float4 channel vectors per CTA (16 channels)
 constexpr int kPS = 5;          // float4 slots per staged pixel (4 used + 1 pad: 80-byte pitch kills the 2-way conflict)
 
 // The reference pads statically for image_size 224 (models/utils.py:126-149): as (top/left) k3s1 1, k5s1 2, k3s2 0, k5s2 1.
-template <int K, int S>
+template <int K, int S, bool SMALL = false>
 struct DwGeo {
     static constexpr int PT = (S == 1) ? (K - 1) / 2 : (K == 3 ? 0 : 1);
-    // forward: output tile and the input region it needs
-    static constexpr int TOY = (S == 1) ? 16 : 8, TOX = 16;
+    // threads per CTA: the 5x5 kernels carry 25 float4 weight-gradient accumulators per thread (~250 registers), so one
+    // CTA per SM is all that fits -- give it 8 warps instead of 4
+    static constexpr int NT = (K == 5 && !SMALL) ? 256 : 128;
+    // forward: output tile and the input region it needs (SMALL: late stages whose whole map is 8x8 or less)
+    static constexpr int TOY = SMALL ? (S == 1 ? 8 : 4) : (S == 1 ? 16 : 8), TOX = SMALL ? 8 : 16;
     static constexpr int FIH = (TOY - 1) * S + K, FIW = (TOX - 1) * S + K;
     // backward: tile of "cells" (a cell = S x S input pixels = one output coordinate) and the output region whose dz1
     // the transposed convolution of those cells touches: rows a + d, d in [DMIN, DMAX]
-    static constexpr int TCY = (S == 1) ? 16 : 8, TCX = 16;
+    static constexpr int TCY = SMALL ? (S == 1 ? 8 : 4) : (S == 1 ? 16 : 8), TCX = SMALL ? 8 : 16;
     static constexpr int DMIN = (S == 1) ? -((K - 1) / 2) : -1;
     static constexpr int DMAX = (S == 1) ? (K - 1) / 2 : (K == 3 ? 0 : 1);
     static constexpr int GH = TCY + DMAX - DMIN, GW = TCX + DMAX - DMIN;
@@ -74,10 +76,11 @@ __device__ __forceinline__ float4 cv_group_sum(float4 v) {
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int K, int S, bool PRE>
-__global__ void __launch_bounds__(kDwT) dw_fwd_fused_kernel(const effdet_dw_fwd_args p, const int tiles_x, const int ntiles,
-                                                            const int tiles_per_cta) {
-    using G = DwGeo<K, S>;
+template <int K, int S, bool PRE, bool SMALL>
+__global__ void __launch_bounds__((DwGeo<K, S, SMALL>::NT)) dw_fwd_fused_kernel(const effdet_dw_fwd_args p, const int tiles_x,
+                                                                                const int ntiles, const int tiles_per_cta) {
+    using G = DwGeo<K, S, SMALL>;
+    constexpr int kDwT = G::NT;
     extern __shared__ __align__(16) float4 dwsm[];
     float4* xs = dwsm;                                   // [FIH*FIW][kPS]
     float4* ws = xs + G::FIH * G::FIW * kPS;             // [K*K][kCVc]
@@ -173,10 +176,11 @@ __global__ void __launch_bounds__(kDwT) dw_fwd_fused_kernel(const effdet_dw_fwd_
 // ------------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------------
-template <int K, int S, bool PRE>
-__global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int ntiles,
-                                                               const int tiles_per_cta) {
-    using G = DwGeo<K, S>;
+template <int K, int S, bool PRE, bool SMALL>
+__global__ void __launch_bounds__((DwGeo<K, S, SMALL>::NT), (DwGeo<K, S, SMALL>::NT == 256 ? 1 : 2))
+dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int ntiles, const int tiles_per_cta) {
+    using G = DwGeo<K, S, SMALL>;
+    constexpr int kDwT = G::NT;
     constexpr int KK = K * K;
     constexpr int NQ = KK + 4;                           // reduced quantities: dW taps, dgamma1, dbeta1, dgamma0, dbeta0
     extern __shared__ __align__(16) float4 dwsm[];
@@ -368,14 +372,16 @@ __global__ void __launch_bounds__(kDwT, 2) dw_bwd_fused_kernel(const effdet_dw_b
     }
 }
 
-template <int K, int S, bool PRE>
+template <int K, int S, bool PRE, bool SMALL>
 static size_t dw_fwd_smem() {
-    using G = DwGeo<K, S>;
+    using G = DwGeo<K, S, SMALL>;
+    constexpr int kDwT = G::NT;
     return (size_t)(G::FIH * G::FIW * kPS + K * K * kCVc + (kDwT / 32) * kCVc) * sizeof(float4);
 }
-template <int K, int S, bool PRE>
+template <int K, int S, bool PRE, bool SMALL>
 static size_t dw_bwd_smem() {
-    using G = DwGeo<K, S>;
+    using G = DwGeo<K, S, SMALL>;
+    constexpr int kDwT = G::NT;
     return (size_t)(2 * G::GH * G::GW * kPS + (PRE ? 2 : 1) * G::BIH * G::BIW * kPS + K * K * kCVc +
                     (K * K + 4) * (kDwT / 32) * kCVc) * sizeof(float4);
 }
@@ -417,27 +423,28 @@ extern "C" int effdet_dwconv_fwd_fused(const effdet_dw_fwd_args* a, int device, 
     EFFDET_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = cdiv(a->C / 4, kCVc);
-#define EFFDET_DWF(K_, S_, PRE_)                                                                                          \
+#define EFFDET_DWF(K_, S_, PRE_, SM_)                                                                                     \
     do {                                                                                                                  \
-        using G = DwGeo<K_, S_>;                                                                                          \
+        using G = DwGeo<K_, S_, SM_>;                                                                                     \
         const int tiles_x = cdiv(a->Wo, G::TOX), tiles_y = cdiv(a->Ho, G::TOY);                                           \
         const int ntiles = tiles_x * tiles_y;                                                                             \
         const int tpc = pick_tiles_per_cta(ntiles, (long long)chunks * a->B);                                             \
-        const size_t smem = dw_fwd_smem<K_, S_, PRE_>();                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(dw_fwd_fused_kernel<K_, S_, PRE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                                  \
+        const size_t smem = dw_fwd_smem<K_, S_, PRE_, SM_>();                                                             \
+        cudaError_t e = cudaFuncSetAttribute(dw_fwd_fused_kernel<K_, S_, PRE_, SM_>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "dwconv_fwd_fused: smem opt-in: %s", cudaGetErrorString(e)); \
-        dw_fwd_fused_kernel<K_, S_, PRE_><<<dim3(chunks, cdiv(ntiles, tpc), a->B), kDwT, smem, st>>>(*a, tiles_x, ntiles, tpc); \
+        dw_fwd_fused_kernel<K_, S_, PRE_, SM_><<<dim3(chunks, cdiv(ntiles, tpc), a->B), G::NT, smem, st>>>(*a, tiles_x, ntiles, tpc); \
     } while (0)
-#define EFFDET_DWF_KS(PRE_)                                                                                               \
+#define EFFDET_DWF_KS(PRE_, SM_)                                                                                          \
     do {                                                                                                                  \
-        if (a->k == 3 && a->stride == 1) EFFDET_DWF(3, 1, PRE_);                                                          \
-        else if (a->k == 3) EFFDET_DWF(3, 2, PRE_);                                                                       \
-        else if (a->stride == 1) EFFDET_DWF(5, 1, PRE_);                                                                  \
-        else EFFDET_DWF(5, 2, PRE_);                                                                                      \
+        if (a->k == 3 && a->stride == 1) EFFDET_DWF(3, 1, PRE_, SM_);                                                     \
+        else if (a->k == 3) EFFDET_DWF(3, 2, PRE_, SM_);                                                                  \
+        else if (a->stride == 1) EFFDET_DWF(5, 1, PRE_, SM_);                                                             \
+        else EFFDET_DWF(5, 2, PRE_, SM_);                                                                                 \
     } while (0)
-    if (a->in_scale) EFFDET_DWF_KS(true);
-    else EFFDET_DWF_KS(false);
+    const bool small = a->Ho <= 8 && a->Wo <= 8;             // late stages: the whole map fits a small tile
+    if (a->in_scale) { if (small) EFFDET_DWF_KS(true, true); else EFFDET_DWF_KS(true, false); }
+    else { if (small) EFFDET_DWF_KS(false, true); else EFFDET_DWF_KS(false, false); }
 #undef EFFDET_DWF_KS
 #undef EFFDET_DWF
     return launch_status("dw_fwd_fused_kernel");
@@ -462,27 +469,28 @@ extern "C" int effdet_dwconv_bwd_fused(const effdet_dw_bwd_args* a, int device, 
     EFFDET_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = cdiv(a->C / 4, kCVc);
-#define EFFDET_DWB(K_, S_, PRE_)                                                                                          \
+#define EFFDET_DWB(K_, S_, PRE_, SM_)                                                                                     \
     do {                                                                                                                  \
-        using G = DwGeo<K_, S_>;                                                                                          \
+        using G = DwGeo<K_, S_, SM_>;                                                                                     \
         const int tiles_x = cdiv(cdiv(a->W, S_), G::TCX), tiles_y = cdiv(cdiv(a->H, S_), G::TCY);                         \
         const int ntiles = tiles_x * tiles_y;                                                                             \
         const int tpc = pick_tiles_per_cta(ntiles, (long long)chunks * a->B);                                             \
-        const size_t smem = dw_bwd_smem<K_, S_, PRE_>();                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(dw_bwd_fused_kernel<K_, S_, PRE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                                  \
+        const size_t smem = dw_bwd_smem<K_, S_, PRE_, SM_>();                                                             \
+        cudaError_t e = cudaFuncSetAttribute(dw_bwd_fused_kernel<K_, S_, PRE_, SM_>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
         if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "dwconv_bwd_fused: smem opt-in: %s", cudaGetErrorString(e)); \
-        dw_bwd_fused_kernel<K_, S_, PRE_><<<dim3(chunks, cdiv(ntiles, tpc), a->B), kDwT, smem, st>>>(*a, tiles_x, ntiles, tpc); \
+        dw_bwd_fused_kernel<K_, S_, PRE_, SM_><<<dim3(chunks, cdiv(ntiles, tpc), a->B), G::NT, smem, st>>>(*a, tiles_x, ntiles, tpc); \
     } while (0)
-#define EFFDET_DWB_KS(PRE_)                                                                                               \
+#define EFFDET_DWB_KS(PRE_, SM_)                                                                                          \
     do {                                                                                                                  \
-        if (a->k == 3 && a->stride == 1) EFFDET_DWB(3, 1, PRE_);                                                          \
-        else if (a->k == 3) EFFDET_DWB(3, 2, PRE_);                                                                       \
-        else if (a->stride == 1) EFFDET_DWB(5, 1, PRE_);                                                                  \
-        else EFFDET_DWB(5, 2, PRE_);                                                                                      \
+        if (a->k == 3 && a->stride == 1) EFFDET_DWB(3, 1, PRE_, SM_);                                                     \
+        else if (a->k == 3) EFFDET_DWB(3, 2, PRE_, SM_);                                                                  \
+        else if (a->stride == 1) EFFDET_DWB(5, 1, PRE_, SM_);                                                             \
+        else EFFDET_DWB(5, 2, PRE_, SM_);                                                                                 \
     } while (0)
-    if (pre) EFFDET_DWB_KS(true);
-    else EFFDET_DWB_KS(false);
+    const bool small = cdiv(a->H, a->stride) <= 8 && cdiv(a->W, a->stride) <= 8;
+    if (pre) { if (small) EFFDET_DWB_KS(true, true); else EFFDET_DWB_KS(true, false); }
+    else { if (small) EFFDET_DWB_KS(false, true); else EFFDET_DWB_KS(false, false); }
 #undef EFFDET_DWB_KS
 #undef EFFDET_DWB
     return launch_status("dw_bwd_fused_kernel");

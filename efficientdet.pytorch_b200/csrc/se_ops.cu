@@ -55,58 +55,63 @@ __global__ void __launch_bounds__(256) se_bwd_dp_kernel(const float* __restrict_
         dp2[(long long)b * C + c] = d;
     }
     __syncthreads();
-    for (int j = warp; j < S; j += 8) {
+    // dp1[j] = sum_c d2[c] * W2[c,j]: lanes run over j (rows of W2 are read coalesced), warps over c, then a
+    // cross-warp reduction through shared memory
+    __shared__ float part[8][33];
+    for (int j0 = 0; j0 < S; j0 += 32) {
+        const int j = j0 + lane;
         float acc = 0.f;
-        for (int c = lane; c < C; c += 32) acc = fmaf(d2[c], __ldg(w2 + (long long)c * S + j), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) dp1[(long long)b * S + j] = acc * swish_gradf_(__ldg(s_pre + (long long)b * S + j));
+        if (j < S)
+            for (int c = warp; c < C; c += 8) acc = fmaf(d2[c], __ldg(w2 + (long long)c * S + j), acc);
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && j < S) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += part[w][lane];
+            dp1[(long long)b * S + j] = t * swish_gradf_(__ldg(s_pre + (long long)b * S + j));
+        }
+        __syncthreads();
     }
 }
 
-// everything that is a sum over the batch or over S, one thread per channel c (grid.y = 0) resp. per (j, c) tile:
-//   dmean[b,c] = sum_j dp1[b,j] W1[j,c];  dW2[c,j] += sum_b dp2[b,c] sw[b,j];  db2[c] += sum_b dp2[b,c];
-//   dW1[j,c] += sum_b dp1[b,j] mean[b,c];  db1[j] += sum_b dp1[b,j]
-__global__ void __launch_bounds__(128) se_bwd_out_kernel(const float* __restrict__ dp2, const float* __restrict__ dp1,
-                                                         const float* __restrict__ mean, const float* __restrict__ s_pre,
-                                                         const float* __restrict__ w1, float* __restrict__ dmean,
-                                                         float* __restrict__ dw1, float* __restrict__ db1,
-                                                         float* __restrict__ dw2, float* __restrict__ db2, int B, int C, int S) {
-    extern __shared__ float sm[];
-    float* p1 = sm;              // [B][S] dp1
-    float* sw = sm + B * S;      // [B][S] swish(s_pre)
-    for (int i = threadIdx.x; i < B * S; i += blockDim.x) {
-        p1[i] = __ldg(dp1 + i);
-        sw[i] = swishf_(__ldg(s_pre + i));
-    }
+// dmean[b,c] = sum_j dp1[b,j] W1[j,c]: one thread per (b, c), W1 rows read coalesced
+__global__ void __launch_bounds__(128) se_bwd_dmean_kernel(const float* __restrict__ dp1, const float* __restrict__ w1,
+                                                           float* __restrict__ dmean, int C, int S) {
+    extern __shared__ float p1[];                      // dp1[b,:]
+    const int b = blockIdx.y;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) p1[j] = __ldg(dp1 + (long long)b * S + j);
     __syncthreads();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < C) {
-        // dmean (per sample) and the b-sums that involve channel c
-        float sb2 = 0.f;
-        for (int b = 0; b < B; ++b) {
-            float acc = 0.f;
-            for (int j = 0; j < S; ++j) acc = fmaf(p1[b * S + j], __ldg(w1 + (long long)j * C + c), acc);
-            dmean[(long long)b * C + c] = acc;
-            sb2 += __ldg(dp2 + (long long)b * C + c);
-        }
-        db2[c] += sb2;
-        for (int j = 0; j < S; ++j) {
-            float a2 = 0.f, a1 = 0.f;
-            for (int b = 0; b < B; ++b) {
-                a2 = fmaf(__ldg(dp2 + (long long)b * C + c), sw[b * S + j], a2);
-                a1 = fmaf(p1[b * S + j], __ldg(mean + (long long)b * C + c), a1);
-            }
-            dw2[(long long)c * S + j] += a2;
-            dw1[(long long)j * C + c] += a1;
-        }
+    if (c >= C) return;
+    float acc = 0.f;
+    for (int j = 0; j < S; ++j) acc = fmaf(p1[j], __ldg(w1 + (long long)j * C + c), acc);
+    dmean[(long long)b * C + c] = acc;
+}
+
+// the sums over the batch, one thread per (c, j):  dW2[c,j] += sum_b dp2[b,c] sw[b,j];  dW1[j,c] += sum_b dp1[b,j] mean[b,c];
+// db2[c] += sum_b dp2[b,c] (threads with j == 0);  db1[j] += sum_b dp1[b,j] (threads with c == 0).  No atomics: every
+// output element has exactly one writer.
+__global__ void __launch_bounds__(128) se_bwd_dw_kernel(const float* __restrict__ dp2, const float* __restrict__ dp1,
+                                                        const float* __restrict__ mean, const float* __restrict__ s_pre,
+                                                        float* __restrict__ dw1, float* __restrict__ db1,
+                                                        float* __restrict__ dw2, float* __restrict__ db2, int B, int C, int S) {
+    const int j = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a2 = 0.f, a1 = 0.f, sb2 = 0.f, sb1 = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float d2 = __ldg(dp2 + (long long)b * C + c);
+        const float d1 = __ldg(dp1 + (long long)b * S + j);
+        a2 = fmaf(d2, swishf_(__ldg(s_pre + (long long)b * S + j)), a2);
+        a1 = fmaf(d1, __ldg(mean + (long long)b * C + c), a1);
+        sb2 += d2;
+        sb1 += d1;
     }
-    if (blockIdx.x == 0) {
-        for (int j = threadIdx.x; j < S; j += blockDim.x) {
-            float s = 0.f;
-            for (int b = 0; b < B; ++b) s += p1[b * S + j];
-            db1[j] += s;
-        }
-    }
+    dw2[(long long)c * S + j] += a2;
+    dw1[(long long)j * C + c] += a1;
+    if (j == 0) db2[c] += sb2;
+    if (c == 0) db1[j] += sb1;
 }
 
 }  // namespace effdet
@@ -131,7 +136,7 @@ extern "C" int effdet_se_gate_bwd(const float* dgate, const float* mean, const f
                                   float* db2, float* ws, int B, int C, int S, int device, effdet_stream_t stream) {
     EFFDET_REQUIRE(dgate && mean && s_pre && gate && w1 && w2 && dmean && dw1 && db1 && dw2 && db2 && ws,
                    "se_gate_bwd: null tensor");
-    EFFDET_REQUIRE(B > 0 && B <= 65535 && C > 0 && S > 0 && (size_t)C * 4 <= 200 * 1024 && (size_t)2 * B * S * 4 <= 200 * 1024,
+    EFFDET_REQUIRE(B > 0 && B <= 65535 && C > 0 && S > 0 && S <= 65535 && (size_t)C * 4 <= 200 * 1024 && (size_t)S * 4 <= 48 * 1024,
                    "se_gate_bwd: bad shape");
     EFFDET_DEVICE(device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -145,11 +150,9 @@ extern "C" int effdet_se_gate_bwd(const float* dgate, const float* mean, const f
     se_bwd_dp_kernel<<<B, 256, sm1, st>>>(dgate, gate, s_pre, w2, dp2, dp1, C, S);
     int s = launch_status("se_bwd_dp_kernel");
     if (s) return s;
-    const size_t sm2 = (size_t)2 * B * S * sizeof(float);
-    if (sm2 > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(se_bwd_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "se_gate_bwd: smem opt-in: %s", cudaGetErrorString(e));
-    }
-    se_bwd_out_kernel<<<cdiv(C, 128), 128, sm2, st>>>(dp2, dp1, mean, s_pre, w1, dmean, dw1, db1, dw2, db2, B, C, S);
-    return launch_status("se_bwd_out_kernel");
+    se_bwd_dmean_kernel<<<dim3(cdiv(C, 128), B), 128, (size_t)S * sizeof(float), st>>>(dp1, w1, dmean, C, S);
+    s = launch_status("se_bwd_dmean_kernel");
+    if (s) return s;
+    se_bwd_dw_kernel<<<dim3(cdiv(C, 128), S), 128, 0, st>>>(dp2, dp1, mean, s_pre, dw1, db1, dw2, db2, B, C, S);
+    return launch_status("se_bwd_dw_kernel");
 }

@@ -106,8 +106,12 @@ __global__ void __launch_bounds__(128) stem_fwd_px_kernel(const float* __restric
 }
 
 constexpr int kStemP = 64;     // pixels staged per iteration
-constexpr int kStemMaxI = 7;   // taps per thread upper bound (27 / (256 / C0)) for C0 <= 64
+constexpr int kStemMaxT = 2;   // taps per thread upper bound: 27 <= 2 * (256 / (C0/4)) for C0 <= 72
 
+// dw[co][tap] += sum_pixels x[pixel + tap] * dz[pixel][co]  -- a 27 x C0 GEMM over ~2 M pixels, shared-memory bound:
+// a thread owns 4 output channels (one 128-bit shared load of dz per pixel) and 1-2 taps (32-bit broadcast loads of
+// the im2col row), i.e. 4 FMAs per 2 shared loads; the previous mapping (1 channel x 4 taps) paid 2 loads per FMA
+// and ran at 0.07 of the HBM roofline.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                          float* __restrict__ dw, int B, int H, int W, int C0, int Ho,
                                                          int Wo) {
@@ -115,12 +119,13 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     float* xs = sm;                    // [kStemP][28]  (27 taps, padded)
     float* ds = sm + kStemP * 28;      // [kStemP][C0]
     const int t = threadIdx.x;
-    const int IG = 256 / C0;           // tap groups
-    const int co = t % C0, ig = t / C0;
-    const bool worker = ig < IG;
-    float acc[kStemMaxI];
+    const int cvs = C0 / 4;            // channel vectors
+    const int ntg = 256 / cvs;         // tap groups
+    const int cv = t % cvs, tg = t / cvs;
+    const bool worker = tg < ntg;
+    float4 acc[kStemMaxT];
 #pragma unroll
-    for (int j = 0; j < kStemMaxI; ++j) acc[j] = 0.f;
+    for (int j = 0; j < kStemMaxT; ++j) acc[j] = f4zero();
     const long long npix = (long long)B * Ho * Wo;
     for (long long p0 = (long long)blockIdx.x * kStemP; p0 < npix; p0 += (long long)gridDim.x * kStemP) {
         for (int i = t; i < kStemP * 27; i += 256) {
@@ -147,13 +152,13 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
         }
         __syncthreads();
         if (worker) {
-#pragma unroll 4
+#pragma unroll 8
             for (int pp = 0; pp < kStemP; ++pp) {
-                const float g = ds[pp * C0 + co];
+                const float4 g = *reinterpret_cast<const float4*>(&ds[pp * C0 + cv * 4]);
 #pragma unroll
-                for (int j = 0; j < kStemMaxI; ++j) {
-                    const int tap = ig + j * IG;
-                    if (tap < 27) acc[j] = fmaf(xs[pp * 28 + tap], g, acc[j]);
+                for (int j = 0; j < kStemMaxT; ++j) {
+                    const int tap = tg + j * ntg;
+                    if (tap < 27) acc[j] = f4fma(make_float4(xs[pp * 28 + tap], xs[pp * 28 + tap], xs[pp * 28 + tap], xs[pp * 28 + tap]), g, acc[j]);
                 }
             }
         }
@@ -161,9 +166,12 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     }
     if (worker) {
 #pragma unroll
-        for (int j = 0; j < kStemMaxI; ++j) {
-            const int tap = ig + j * IG;
-            if (tap < 27) atomicAdd(dw + co * 27 + tap, acc[j]);
+        for (int j = 0; j < kStemMaxT; ++j) {
+            const int tap = tg + j * ntg;
+            if (tap < 27) {
+                float* o = dw + (cv * 4) * 27 + tap;
+                atomicAdd(o, acc[j].x); atomicAdd(o + 27, acc[j].y); atomicAdd(o + 54, acc[j].z); atomicAdd(o + 81, acc[j].w);
+            }
         }
     }
 }
@@ -206,7 +214,7 @@ extern "C" int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw
     const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
     const long long npix = (long long)B * Ho * Wo;
     int blocks = cdiv(npix, kStemP);
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 8) blocks = 148 * 8;
     const size_t smem = (size_t)kStemP * (28 + C0) * sizeof(float);
     stem_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo);
     return launch_status("stem_wgrad_kernel");
