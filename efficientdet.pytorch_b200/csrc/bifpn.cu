@@ -8,6 +8,8 @@
 // up-node, 4*B*C*(s^2 + 4 s^2 + [s^2] + s^2) for a pool-node.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace effdet {
 
 struct FuseCoef { float n0, n1, n2, D; };
@@ -66,7 +68,19 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(const effdet_fuse_args p)
         const float4 c = ldg4(p.c + idx * 4);
         s = make_float4(s.x + k.n2 * c.x, s.y + k.n2 * c.y, s.z + k.n2 * c.z, s.w + k.n2 * c.w);
     }
-    st4(p.out + idx * 4, make_float4(s.x / k.D, s.y / k.D, s.z / k.D, s.w / k.D));
+    const float4 o = make_float4(s.x / k.D, s.y / k.D, s.z / k.D, s.w / k.D);
+    if (p.out) st4(p.out + idx * 4, o);
+    if (p.out_planes) {          // the node conv's operand format: bf16 hi/lo planes [2][B*H*W][pitch], o ~= hi + lo
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - __low2float(h0), o.y - __high2float(h0));
+        const __nv_bfloat162 l1 = __floats2bfloat162_rn(o.z - __low2float(h1), o.w - __high2float(h1));
+        const int pitch = (p.C + 7) / 8 * 8;
+        __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(p.out_planes);
+        const long long e = (idx / cvecs) * pitch + cv * 4;
+        *reinterpret_cast<uint2*>(pl + e) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(pl + (long long)p.B * p.H * p.W * pitch + e) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
 }
 
 __device__ __forceinline__ void put4(float* dst, float4 v, int acc) {
@@ -195,7 +209,8 @@ __global__ void fuse_bwd_weights_kernel(const float* __restrict__ w, int stride,
 using namespace effdet;
 
 extern "C" int effdet_bifpn_fuse_fwd(const effdet_fuse_args* a, int device, effdet_stream_t stream) {
-    EFFDET_REQUIRE(a && a->a && a->b && a->w && a->out, "bifpn_fuse_fwd: null tensor");
+    EFFDET_REQUIRE(a && a->a && a->b && a->w && (a->out || a->out_planes), "bifpn_fuse_fwd: null tensor");
+    EFFDET_REQUIRE(aligned16(a->out_planes), "bifpn_fuse_fwd: alignment");
     EFFDET_REQUIRE(a->C % 4 == 0 && a->B > 0 && a->H > 0 && a->W > 0, "bifpn_fuse_fwd: bad shape");
     EFFDET_REQUIRE(a->mode == EFFDET_FUSE_POOL || (a->H % 2 == 0 && a->W % 2 == 0), "bifpn_fuse_fwd: up-node needs even H,W");
     EFFDET_REQUIRE(aligned16(a->a) && aligned16(a->b) && aligned16(a->c) && aligned16(a->out), "bifpn_fuse_fwd: alignment");

@@ -22,12 +22,15 @@ namespace effdet {
 
 constexpr int kPlMaxLevels = 8;
 constexpr int kPlThreads = 192;
-constexpr int kPlBN = 256;
-constexpr int kPlStages = 2;
 constexpr int kPlA = 128 * 128;            // one plane of the activation tile: 128 pixel rows x 64 channels (bf16)
-constexpr int kPlB = kPlBN * 128;          // one plane of the weight tile: 256 output channels x 64 input channels
-constexpr int kPlStage = 2 * kPlA + 2 * kPlB;
-constexpr int kPlSmem = kPlStages * kPlStage + 1024 + 256 + kPlBN * 4;
+// BN = output channels per tile (TMEM: 2 x BN columns); the ring depth is what fits next to it
+template <int BN>
+struct PlCfg {
+    static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int kB = BN * 128;    // one plane of the weight tile: BN output channels x 64 input channels
+    static constexpr int kStage = 2 * kPlA + 2 * kB;
+    static constexpr int kSmem = kStages * kStage + 1024 + 256 + BN * 4;
+};
 
 struct PlLevel {
     int B, H, W;
@@ -52,8 +55,10 @@ struct PlMaps {
     CUtensorMap x[kPlMaxLevels];
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kPlThreads, 1)
 conv_planes_kernel(const __grid_constant__ PlMaps maps, const __grid_constant__ CUtensorMap wmap, const __grid_constant__ PlArgs P) {
+    constexpr int kPlBN = BN, kPlStages = PlCfg<BN>::kStages, kPlB = PlCfg<BN>::kB, kPlStage = PlCfg<BN>::kStage;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPlStages * kPlStage);
@@ -423,11 +428,12 @@ extern "C" int effdet_conv_planes_multi(const effdet_conv_planes_args* levels, i
     }
     const int taps = a0->ksize * a0->ksize;
     const int kpad = conv_tc_kpad(a0->Cin);
+    const int BN = a0->Cout <= 64 ? 64 : (a0->Cout <= 128 ? 128 : 256);
     CUtensorMap wmap;
     {
         const cuuint64_t gdim[3] = {(cuuint64_t)taps * kpad, (cuuint64_t)a0->Cout, 2};
         const cuuint64_t gstr[2] = {(cuuint64_t)taps * kpad * 2, (cuuint64_t)a0->Cout * taps * kpad * 2};
-        const cuuint32_t box[3] = {64, (cuuint32_t)kPlBN, 1};
+        const cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a0->w_tc), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -435,16 +441,24 @@ extern "C" int effdet_conv_planes_multi(const effdet_conv_planes_args* levels, i
         if (r != CUDA_SUCCESS) return fail(EFFDET_ERR_LAUNCH, "conv_planes_multi: tensor map of the weights failed (%d)", (int)r);
     }
     P.nlevels = nlevels;
-    P.ntn = cdiv(a0->Cout, kPlBN);
+    P.ntn = cdiv(a0->Cout, BN);
     P.total_tiles = tiles * P.ntn;
     P.Cin = a0->Cin; P.Cout = a0->Cout; P.ksize = a0->ksize; P.act = a0->act;
     P.kblocks = kpad / 64;
     P.opitch = opitch;
     P.bias = a0->bias;
     P.colsum = a0->colsum;
-    cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlSmem);
-    if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv_planes_multi: smem opt-in: %s", cudaGetErrorString(e));
     const int grid = P.total_tiles < 148 ? P.total_tiles : 148;
-    conv_planes_kernel<<<grid, kPlThreads, kPlSmem, (cudaStream_t)stream>>>(maps, wmap, P);
+#define EFFDET_PL_LAUNCH(BN_)                                                                                              \
+    do {                                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(conv_planes_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                             PlCfg<BN_>::kSmem);                                                          \
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "conv_planes_multi: smem opt-in: %s", cudaGetErrorString(e)); \
+        conv_planes_kernel<BN_><<<grid, kPlThreads, PlCfg<BN_>::kSmem, (cudaStream_t)stream>>>(maps, wmap, P);             \
+    } while (0)
+    if (BN == 64) EFFDET_PL_LAUNCH(64);
+    else if (BN == 128) EFFDET_PL_LAUNCH(128);
+    else EFFDET_PL_LAUNCH(256);
+#undef EFFDET_PL_LAUNCH
     return launch_status("conv_planes_kernel");
 }

@@ -114,7 +114,7 @@ class DwBwdArgs(ctypes.Structure):
 
 class FuseArgs(ctypes.Structure):
     _fields_ = [('a', _P), ('b', _P), ('c', _P), ('w', _P), ('w_stride', _I32), ('eps', _F), ('out', _P),
-                ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('mode', _I32)]
+                ('B', _I32), ('H', _I32), ('W', _I32), ('C', _I32), ('mode', _I32), ('out_planes', _P)]
 
 
 class FuseBwdArgs(ctypes.Structure):

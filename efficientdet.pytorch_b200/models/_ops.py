@@ -546,7 +546,7 @@ class ConvBiasActFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 
 
-def _fuse_fwd(a, b, c, w, col, eps, mode):
+def _fuse_fwd(a, b, c, w, col, eps, mode, planes=False):
     B, H, W, C = a.shape
     # the reference fails with a shape mismatch in `w*in + w*F.interpolate(...)` (models/bifpn.py:188-201) when the
     # pyramid does not halve exactly; the kernels index b as [y//2, x//2] / [2y+dy, 2x+dx], so refuse the same inputs
@@ -554,9 +554,10 @@ def _fuse_fwd(a, b, c, w, col, eps, mode):
     if tuple(b.shape) != want or (mode == FUSE_UP and (H % 2 or W % 2)) or (c is not None and c.shape != a.shape):
         raise N.EffdetNativeError('BiFPN levels must halve exactly (image height and width multiples of 128): node '
                                   'input %s cannot be fused with %s' % (tuple(a.shape), tuple(b.shape)))
-    out = torch.empty_like(a)
+    out = _planes(B, H, W, C, a) if planes else torch.empty_like(a)      # planes: the node conv's TMA operand format
     wst = w.shape[1]
-    args = N.FuseArgs(N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, N.f32(out), B, H, W, C, mode)
+    args = N.FuseArgs(N.f32(a), N.f32(b), N.f32(c), w.data_ptr() + 4 * col, wst, eps, None if planes else N.f32(out),
+                      B, H, W, C, mode, N.ptr(out) if planes else None)
     N.call('effdet_bifpn_fuse_fwd', a, args,
            nbytes=4.0 * (2 * a.numel() + b.numel() + (c.numel() if c is not None else 0)))
     return out
@@ -584,7 +585,18 @@ class BiFPNLayerFn(torch.autograd.Function):
         w1c, w2c = _contig(w1.detach()), _contig(w2.detach())
         C = ins[0].shape[3]
 
-        def conv(idx, f):
+        # tensor-core mode: the fused map is written as bf16 hi/lo planes and the node conv is the TMA-fed planes
+        # kernel (no gather, no split pass in the weight gradient); every level must admit a TMA pixel box
+        pl = (tc_enabled() and C % 4 == 0 and os.environ.get('EFFDET_B200_BIFPN_PLANES', '1') != '0' and
+              all(N.load().effdet_wgrad_tc_geometry_ok(t.shape[0], t.shape[1], t.shape[2]) for t in ins))
+
+        def conv(idx, f, like):
+            if pl:
+                B_, H_, W_, _ = like.shape
+                y = _empty((B_, H_, W_, C), like)
+                conv_planes_multi(like, [dict(x=f, y_ptr=N.f32(y), y_bs=H_ * W_ * C, B=B_, H=H_, W=W_)],
+                                  tc_packs(convs[2 * idx])[0], C, C, 3, bias=convs[2 * idx + 1].detach())
+                return y
             wf, _ = pack_conv(convs[2 * idx])
             return conv2d(f, wf, C, 3, bias=convs[2 * idx + 1].detach(), w_tc=tc_packs(convs[2 * idx])[0])
 
@@ -593,21 +605,21 @@ class BiFPNLayerFn(torch.autograd.Function):
         td[L - 1] = ins[L - 1]
         idx = 0
         for i in range(L - 1, 0, -1):                       # top-down
-            f = _fuse_fwd(ins[i - 1], td[i], None, w1c, i - 1, eps, FUSE_UP)
+            f = _fuse_fwd(ins[i - 1], td[i], None, w1c, i - 1, eps, FUSE_UP, planes=pl)
             fused[idx] = f
-            td[i - 1] = conv(idx, f)
+            td[i - 1] = conv(idx, f, ins[i - 1])
             idx += 1
         out = [None] * L
         out[0] = td[0]
         for i in range(0, L - 2):                           # bottom-up
-            f = _fuse_fwd(td[i + 1], out[i], ins[i + 1], w2c, i, eps, FUSE_POOL)
+            f = _fuse_fwd(td[i + 1], out[i], ins[i + 1], w2c, i, eps, FUSE_POOL, planes=pl)
             fused[idx] = f
-            out[i + 1] = conv(idx, f)
+            out[i + 1] = conv(idx, f, td[i + 1])
             idx += 1
-        f = _fuse_fwd(ins[L - 1], out[L - 2], None, w1c, L - 1, eps, FUSE_POOL)   # top level
+        f = _fuse_fwd(ins[L - 1], out[L - 2], None, w1c, L - 1, eps, FUSE_POOL, planes=pl)   # top level
         fused[idx] = f
-        out[L - 1] = conv(idx, f)
-        ctx.eps, ctx.L = eps, L
+        out[L - 1] = conv(idx, f, ins[L - 1])
+        ctx.eps, ctx.L, ctx.pl = eps, L, pl
         ctx.keep = (ins, td, out, fused, w1, w2, w1c, w2c, convs)
         return tuple(out)
 
@@ -624,8 +636,16 @@ class BiFPNLayerFn(torch.autograd.Function):
         def conv_bwd(idx, dy):
             w, b = convs[2 * idx], convs[2 * idx + 1]
             dw, db = zb[2 + 2 * idx], zb[3 + 2 * idx]
-            conv_wgrad(fused[idx], dy, dw, db, 3, tc=tc_enabled())
             dconv[2 * idx], dconv[2 * idx + 1] = dw, db
+            if ctx.pl:
+                B_, H_, W_, _ = dy.shape
+                dyp = _planes(B_, H_, W_, C, dy)           # one pass: planes of dy + the bias gradient (column sums)
+                to_planes(N.f32(dy), H_ * W_ * C, dyp, B_, H_ * W_, C, dy, colsum=db)
+                wgrad_planes_multi(dy, [dict(x=fused[idx], dy=dyp, B=B_, H=H_, W=W_)], dw, C, C, 3)
+                df = _empty((B_, H_, W_, C), dy)
+                conv_planes_multi(dy, [dict(x=dyp, y_ptr=N.f32(df), y_bs=H_ * W_ * C, B=B_, H=H_, W=W_)], tc_packs(w)[1], C, C, 3)
+                return df
+            conv_wgrad(fused[idx], dy, dw, db, 3, tc=tc_enabled())
             _, wd = pack_conv(w)
             return conv2d(dy, wd, C, 3, w_tc=tc_packs(w)[1])
 

@@ -1,0 +1,63 @@
+"""CUDA-graph execution of the training step (forward + FocalLoss + backward, optionally the fused optimizer).
+
+Every kernel of the hot path is launched on the caller's stream with device-resident arguments and no host
+synchronisation (the C ABI never syncs, FocalLoss reads its upstream gradients from device memory), so the ~480
+launches of a step can be captured once and replayed: the host cost of a step drops from ~12-16 ms of ctypes calls to
+one cudaGraphLaunch, which matters as soon as the GPU finishes a step faster than Python can issue it.
+
+    step = GraphedTrainStep(model, images_example, annotations_example)          # model.train(); freeze_bn() first
+    loss = step(images, annotations)      # copies into the static inputs, replays, returns the static loss tensor
+    ... model parameters' .grad now hold this step's gradients (same tensors every step)
+
+Shapes are static (the reference pads every batch to the common size and a fixed annotation count per batch can be
+obtained by padding with -1 rows, which FocalLoss ignores).  Drop-connect keeps working: torch.rand inside a captured
+region advances the Philox offset on every replay.  With `optimizer=FusedClipAdamW(...)` the clip + AdamW launches are
+captured too; the packed-weight / folded-BN derivations are then captured as well (they must re-run every step because
+the weights change without Python seeing it).
+"""
+import torch
+
+from . import _ops
+
+
+class GraphedTrainStep:
+    def __init__(self, model, images, annotations, optimizer=None, warmup=3):
+        if not images.is_cuda:
+            raise _ops.N.EffdetNativeError('GraphedTrainStep needs CUDA example inputs')
+        self.model = model
+        self.optimizer = optimizer
+        self.static_images = images.clone()
+        self.static_annots = annotations.clone()
+        params = [p for p in model.parameters() if p.requires_grad]
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream(images.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                                   # fills allocator pools, caches, cuFuncSetAttribute
+                self._eager_step(params)
+        torch.cuda.current_stream(images.device).wait_stream(side)
+        torch.cuda.synchronize(images.device)
+        if optimizer is not None:
+            _ops.invalidate_caches()                                  # capture the weight re-packing with the step
+        self.graph = torch.cuda.CUDAGraph()
+        for p in params:
+            p.grad = None
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._eager_step(params, zero=False)
+        self.params = params
+
+    def _eager_step(self, params, zero=True):
+        if zero:
+            for p in params:
+                p.grad = None
+        cl, rl = self.model([self.static_images, self.static_annots])
+        loss = cl.mean() + rl.mean()
+        loss.backward()
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss.detach()
+
+    def __call__(self, images, annotations):
+        self.static_images.copy_(images, non_blocking=True)
+        self.static_annots.copy_(annotations, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

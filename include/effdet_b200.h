@@ -289,6 +289,8 @@ typedef struct {
     const float* w; int32_t w_stride; float eps;
     float* out;
     int32_t B, H, W, C, mode; /* H,W = resolution of a/out */
+    void* out_planes;         /* optional: the fused map as bf16 hi/lo planes [2][B*H*W][pitch(C)] (the node conv's TMA
+                                 operand, effdet_conv_planes_multi); `out` may then be NULL */
 } effdet_fuse_args;
 int effdet_bifpn_fuse_fwd(const effdet_fuse_args* a, int device, effdet_stream_t stream);
 

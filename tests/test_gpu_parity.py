@@ -20,13 +20,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north_star tolerance (forward outputs, losses)
 TOL_EXACT = 5e-5    # what the exact-fp32 kernels must reach (atomics / summation order only)
 # End-to-end GRADIENT tolerance.  Gradients of this network are ill-conditioned w.r.t. forward round-off:
-# injecting 1e-5 relative noise into the head conv outputs of the fp32 CPU oracle moves the stem weight
-# gradient by 8.5e-3 (DESIGN.md "Gradient conditioning", measured with the script quoted there), i.e.
-# ~850x amplification.  The bf16x3 tensor-core convs carry ~5e-6 per layer (kernel-level tests hold them
-# to 3e-5), the exact-fp32 path ~1e-7; the bounds below are those noise levels times the amplification, with
-# head-room for run-to-run variation (fp32 atomics order, ReLU / max-pool / IoU-threshold decisions that sit
-# within round-off of their switching point).
-TOL_GRAD = {'fp32': 5e-3, 'bf16x3': 5e-2}
+# tools/grad_conditioning.py (output committed as profiles/r02_grad_conditioning.txt) multiplies every conv output of
+# the fp32 CPU oracle by (1 + 5e-6 * N(0,1)) -- the per-layer error the bf16x3 tensor-core products measure at
+# (test_conv2d_tensor_core_forward_dgrad_wgrad holds them to 3e-5) -- and the worst parameter gradient moves by 1.3e-2
+# (amplification ~2600x: the regression tower, where smooth-L1 / ReLU decisions sit within round-off of their
+# switching point), the median one by 2.8e-4.  The bf16x3 bound below is that noise level times 1.5; the exact-fp32
+# path carries ~1e-7 per layer.  Measured worst on B200: 4.4e-3 (D0 512 train mode), 8.8e-3 (B=2 golden, empty image).
+TOL_GRAD = {'fp32': 5e-3, 'bf16x3': 2e-2}
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
@@ -442,15 +442,17 @@ def test_drop_connect_uses_same_rng_stream():
         assert _rel(o.detach().cpu(), r) < TOL_EXACT
 
 
-@pytest.mark.parametrize('W,D', [(64, 2), (88, 1)])
-def test_bifpn_forward_backward(W, D, prec):
+@pytest.mark.parametrize('W,D,B', [(64, 2, 2), (88, 1, 2), (64, 2, 4), (224, 1, 4), (384, 1, 4)])
+def test_bifpn_forward_backward(W, D, B, prec):
+    """B=2: the 2x2 level has no legal TMA pixel box -> gather kernels; B=4: every level qualifies -> in tensor-core
+    mode the fused maps are bf16 planes and the node convs run on conv_planes_kernel<64/128/256> (1 or 2 channel tiles)"""
     from models.bifpn import BIFPN
     cfg = O.make_config('efficientdet-d0', 20, W, D)
     sd = O.init_state_dict(cfg, seed=21)
     chans = cfg['stage_out'][-5:]
     m = _load(BIFPN(in_channels=chans, out_channels=W, stack=D, num_outs=5), sd, 'neck.')
     g = torch.Generator().manual_seed(2)
-    feats = [torch.randn(2, c, 32 >> i, 32 >> i, generator=g) for i, c in enumerate(chans)]
+    feats = [torch.randn(B, c, 32 >> i, 32 >> i, generator=g) for i, c in enumerate(chans)]
     fr = [f.clone().requires_grad_(True) for f in feats]
     fd = [f.to(_dev()).requires_grad_(True) for f in feats]
     sdg = _grad_sd(sd)
@@ -998,3 +1000,29 @@ def test_checkpoint_save_resume_round_trip(tmp_path):
     worst = max(_rel(pb, pa) for pa, pb in zip(a.parameters(), b.parameters()))
     assert worst < 2e-4, worst        # one more optimizer step each; fp32 atomics order differs between the two runs
     assert int(opt_b.state[next(iter(b.parameters()))]['step']) == 3
+
+
+def test_graphed_train_step_equals_eager():
+    """models/graph_step.py: the captured step (forward + loss + backward as one CUDA graph) reproduces the eager step
+    on new inputs copied into its static buffers: same loss, same gradients (fp32 atomics order aside)."""
+    from models.graph_step import GraphedTrainStep
+    cfg = O.make_config('efficientdet-d0', num_classes=20, W_bifpn=64, D_bifpn=2)
+    sd = O.init_state_dict(cfg, seed=13)
+    m = _build('efficientdet-d0', 20, 64, 2, sd, is_training=True)
+    m.eval()                                                  # drop-connect off: eager and replay must see the same function
+    m.is_training = True
+    batches = [O.synthetic_batch(2, size=256, num_classes=20, seed=s_) for s_ in (20, 21)]
+    eager = []
+    for images, ann in batches:
+        for p in m.parameters():
+            p.grad = None
+        cl, rl = m([images.to(_dev()), ann.to(_dev())])
+        (cl.mean() + rl.mean()).backward()
+        eager.append((float(cl + rl), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    step = GraphedTrainStep(m, batches[0][0].to(_dev()), batches[0][1].to(_dev()))
+    for (images, ann), (loss_e, grads_e) in zip(batches, eager):
+        loss = step(images.to(_dev()), ann.to(_dev()))
+        torch.cuda.synchronize()
+        assert abs(float(loss) - loss_e) <= 1e-4 * abs(loss_e)
+        worst = max(_rel(p.grad, grads_e[k]) for k, p in m.named_parameters() if k in grads_e)
+        assert worst < 1e-3, worst

@@ -112,15 +112,19 @@ class Recorder:
                 px, kk = a['H'] * a['W'], a['ksize'] ** 2
                 self.need(a['x'], (a['B'] - 1) * a['x_bstride'] + px * a['Cin'], name + ' x')
                 self.need(a['dy'], (a['B'] - 1) * a['dy_bstride'] + px * a['Cout'], name + ' dy')
-                assert (a['dy'] is None) == (a['dy_planes'] is not None)
-                if a['dy_planes'] is not None:
-                    assert a['precision'] == 1 and a['dbias'] is None and a['Cout'] % 8 == 0
-                    self.need(a['dy_planes'], a['B'] * px * a['Cout'], name + ' dy_planes')
+                assert (a['dy'] is None) == (a['dy_planes'] is not None) and (a['x'] is None) == (a['x_planes'] is not None)
+                pitch = lambda c: (c + 7) // 8 * 8                                       # noqa: E731
+                if a['dy_planes'] is not None:                 # bf16 hi/lo planes [2][B*H*W][pitch]: 4 bytes per element
+                    assert a['precision'] == 1 and a['dbias'] is None
+                    self.need(a['dy_planes'], a['B'] * px * pitch(a['Cout']), name + ' dy_planes')
+                if a['x_planes'] is not None:
+                    assert a['precision'] == 1 and a['a_scale'] is None and a['in_scale'] is None
+                    self.need(a['x_planes'], a['B'] * px * pitch(a['Cin']), name + ' x_planes')
                 self.need(a['dw'], kk * a['Cin'] * a['Cout'], name + ' dw')
                 self.need(a['dbias'], a['Cout'], name + ' dbias')
                 self.need(a['a_scale'], a['B'] * a['Cin'], name + ' a_scale')
                 self.need(a['in_scale'], a['Cin'], name + ' in_scale'); self.need(a['in_shift'], a['Cin'], name + ' in_shift')
-                assert (a['ws_x'] is None) == (a['precision'] == 0)
+                assert (a['ws_x'] is None) == (a['precision'] == 0 or a['x_planes'] is not None)
                 assert (a['ws_dy'] is None) == (a['precision'] == 0 or a['dy_planes'] is not None)
         elif name in ('effdet_dwconv_fwd', 'effdet_dwconv_bwd_data', 'effdet_dwconv_bwd_weight'):
             B, H, W, C, k, stride, pad_t, pad_l, Ho, Wo = snap[-10:]
@@ -143,6 +147,24 @@ class Recorder:
             else:
                 x, dz, dw = snap[:3]
                 self.need(x, big, 'dw x'); self.need(dz, small, 'dw dz'); self.need(dw, k * k * C, 'dw dw')
+        elif name == 'effdet_conv_planes_multi':
+            levels = snap[0]
+            assert snap[1] == len(levels) and 1 <= len(levels) <= 8
+            pitch = lambda c: (c + 7) // 8 * 8                                           # noqa: E731
+            for a in levels:
+                px = a['H'] * a['W']
+                assert a['ksize'] in (1, 3) and a['Cin'] % 4 == 0 and a['Cout'] % 4 == 0 and a['w_tc'] is not None
+                assert a['y'] is not None or a['y_planes'] is not None
+                self.need(a['x_planes'], a['B'] * px * pitch(a['Cin']), name + ' x_planes')
+                self.need(a['y_planes'], a['B'] * px * pitch(a['Cout']), name + ' y_planes')
+                self.need(a['mask_planes'], a['B'] * px * pitch(a['Cout']), name + ' mask_planes')
+                self.need(a['y'], (a['B'] - 1) * a['y_bstride'] + px * a['Cout'], name + ' y')
+                self.need(a['residual'], (a['B'] - 1) * a['r_bstride'] + px * a['Cout'], name + ' residual')
+                self.need(a['bias'], a['Cout'], name + ' bias'); self.need(a['colsum'], a['Cout'], name + ' colsum')
+        elif name == 'effdet_to_planes':
+            x, x_bs, prob, p_bs, planes, colsum, B, HW, C = snap
+            self.need(x, (B - 1) * x_bs + HW * C, 'to_planes x'); self.need(prob, (B - 1) * p_bs + HW * C, 'to_planes prob')
+            self.need(planes, B * HW * ((C + 7) // 8 * 8), 'to_planes planes'); self.need(colsum, C, 'to_planes colsum')
         elif name in ('effdet_dwconv_fwd_fused', 'effdet_dwconv_bwd_fused'):
             a = snap[0]
             B, H, W, C, k, stride, Ho, Wo = (a[f] for f in ('B', 'H', 'W', 'C', 'k', 'stride', 'Ho', 'Wo'))
@@ -276,7 +298,10 @@ def test_train_step_call_trace_matches_the_gpu_profile(traced):
     m.train()
     m.is_training = True
     m.freeze_bn()
-    images, ann = O.synthetic_batch(2, size=256, num_classes=80, seed=3)
+    # the bench geometry (bs 32, 512x512): path decisions that depend on the map sizes (planes-based head, TMA pixel
+    # boxes, small-map depthwise tiles) are then the ones the B200 run took; nothing is computed, torch.empty() of the
+    # multi-GB activations only reserves address space
+    images, ann = O.synthetic_batch(32, size=512, num_classes=80, seed=3)
 
     def step():
         for p in m.parameters():
