@@ -409,8 +409,8 @@ def run_ours(args):
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms else 0.0
         tc = _ops.tc_enabled()
         peak = peaks['bf16_tflops_sustained'] or peaks['bf16_tflops']
-        roofline = dict(kernel=('conv_tc_multi_kernel / conv_tc_kernel: tcgen05 bf16x3 implicit GEMM (3 kind::f16 MMAs per product, fp32 '
-                                'accum in TMEM), dense 3x3 convs of head+neck, fwd+dgrad' if tc else
+        roofline = dict(kernel=('conv_planes_kernel: TMA-fed tcgen05 bf16x3 implicit GEMM on bf16 hi/lo planes (3 kind::f16 MMAs per '
+                                'product, fp32 accum in TMEM), dense 3x3 convs of head+neck, fwd+dgrad' if tc else
                                 'conv_igemm_kernel: exact fp32 on the CUDA cores, dense 3x3 convs of head+neck, fwd+dgrad'),
                         bound='tensor', achieved=round(ach, 2), peak=peak, unit='TFLOP/s', frac=round(ach / peak, 4),
                         peak_source=peaks['source'] + ' bf16 cuBLAS, sustained figure (kernel timed inside a long step)',
@@ -418,7 +418,7 @@ def run_ours(args):
                               '(bf16 hi/lo split for <=1e-3 parity): tensor-pipe work = %.0f TFLOP/s = %.2f of peak'
                               % (3 * ach, 3 * ach / peak)) if tc else None,
                         launches_per_step=n // psteps, ms_per_step=round(t_ms / psteps, 3),
-                        traffic=measured_traffic('conv_tc_multi_kernel<256,2>') if tc else None)
+                        traffic=measured_traffic('conv_planes_kernel<256> 256->256') if tc else None)
         if not args.no_cpu and world == 1:      # the CPU leg is an N=1 measurement (the host cores are shared by all ranks)
             if train:
                 cpu_base = cpu_baseline_subprocess(args.config, 5 if args.config == 'd0' else 1, 1, 8 if args.config == 'd0' else 1,

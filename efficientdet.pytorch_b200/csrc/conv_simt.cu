@@ -17,6 +17,8 @@ bool wgrad_tc_eligible(const effdet_wgrad_args* a);
 // persistent pointwise GEMM (pw_gemm.cu)
 bool pw_gemm_eligible(const effdet_conv_args* a);
 int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st);
+bool pw_wgrad_eligible(const effdet_wgrad_args* a);
+int pw_wgrad_launch(const effdet_wgrad_args* a, cudaStream_t st);
 int wgrad_tc_launch(const effdet_wgrad_args* a, cudaStream_t st, bool* dbias_done);
 
 constexpr int kBM = 128;   // output pixels per CTA
@@ -453,7 +455,9 @@ extern "C" int effdet_conv2d_wgrad(const effdet_wgrad_args* a, int device, effde
     cudaStream_t st = (cudaStream_t)stream;
     int s = EFFDET_OK;
     bool dbias_done = false;
-    if (wgrad_tc_eligible(a)) {
+    if (pw_wgrad_eligible(a)) {
+        s = pw_wgrad_launch(a, st);      // 1x1, no bias: operands converted in the kernel, no split passes
+    } else if (wgrad_tc_eligible(a)) {
         s = wgrad_tc_launch(a, st, &dbias_done);
     } else if (a->dy_planes || a->x_planes) {
         return fail(EFFDET_ERR_UNSUPPORTED, "wgrad: dy_planes given but the TMA-fed tensor-core kernel cannot take this shape "

@@ -302,9 +302,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (lane == 0) mbar_arrive(&acc_empty[acc]);
                 }
                 if (P.tma_store) {
+                    // every warp stages and stores ITS 32 rows (a 4 KB, 1024-byte aligned slice of the staging buffer) on its
+                    // own: no CTA-wide barrier in the store path, the four warps drift freely (bulk groups are per thread)
                     uint8_t* buf = outst + (nstore % P.nout) * kPwOut;
-                    if (etid == 0) tma_store_wait_read_upto<kPwMaxOut - 1>(P.nout - 1);   // the store that last used this buffer has read it
-                    named_bar_sync(1, 128);
+                    if (lane == 0) tma_store_wait_read_upto<kPwMaxOut - 1>(P.nout - 1);   // this warp's store that last used the slot
+                    __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float4 v = make_float4(__uint_as_float(v32[q * 4]), __uint_as_float(v32[q * 4 + 1]),
@@ -313,9 +315,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         *reinterpret_cast<float4*>(buf + r * 128 + ((q ^ (r & 7)) << 4)) = v;
                     }
                     fence_proxy_async();
-                    named_bar_sync(1, 128);
-                    if (etid == 0) {
-                        tma_store_2d(&map_y, buf, n0 + cc * 32, m0);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&map_y, buf + quarter * 4096, n0 + cc * 32, m0 + quarter * 32);
                         tma_store_commit();
                     }
                     ++nstore;
@@ -349,7 +351,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
         }
-        if (P.tma_store && etid == 0) tma_store_wait_read<0>();     // shared memory stays valid until the last store has read it
+        if (P.tma_store && lane == 0) tma_store_wait_read<0>();     // shared memory stays valid until the last store has read it
     }
     tc_fence_before();
     __syncthreads();
@@ -456,7 +458,7 @@ int pw_gemm_launch(const effdet_conv_args* a, cudaStream_t st) {
     if (P.tma_store) {
         const cuuint64_t gdim[2] = {(cuuint64_t)a->Cout, (cuuint64_t)P.M};
         const cuuint64_t gstr[1] = {(cuuint64_t)a->Cout * 4};
-        const cuuint32_t box[2] = {32, 128};
+        const cuuint32_t box[2] = {32, 32};              // one epilogue warp's rows
         const cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a->y, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

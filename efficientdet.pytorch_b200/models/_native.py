@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_HERE, '..', 'csrc'))
 SO_PATH = os.path.join(CSRC, 'libeffdet_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_planes.cu', 'pw_gemm.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'se_ops.cu', 'bifpn.cu', 'pipeline.cu',
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_planes.cu', 'pw_gemm.cu', 'pw_wgrad.cu', 'stem.cu', 'depthwise.cu', 'dw_fused.cu', 'mbconv_ops.cu', 'se_ops.cu', 'bifpn.cu', 'pipeline.cu',
            'loss.cu', 'detect.cu', 'layout.cu', 'optim.cu']
 NVCC_FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-Xcompiler', '-fPIC', '-shared']
@@ -284,7 +284,7 @@ class Profiler:
     def conv_flops(self, pred):
         fl, ms_tot, n = 0.0, 0.0, 0
         for name, t, ms in self._ms():
-            if name in ('effdet_conv2d', 'effdet_conv2d_multi') and t is not None and pred(t):
+            if name in ('effdet_conv2d', 'effdet_conv2d_multi', 'effdet_conv_planes_multi') and t is not None and pred(t):
                 fl += 2.0 * t[0] * t[1] * t[2] * t[5] * t[5] * t[3] * t[4]
                 ms_tot += ms
                 n += 1
@@ -310,7 +310,7 @@ def call(name, dev_tensor, *args, nbytes=0, flops=0):
         if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
             a = args[0]
             tag = (a.B, a.H, a.W, a.Cin, a.Cout, a.ksize)
-        elif name in ('effdet_conv2d_multi', 'effdet_conv2d_wgrad_multi'):
+        elif name in ('effdet_conv2d_multi', 'effdet_conv2d_wgrad_multi', 'effdet_conv_planes_multi'):
             arr, nl = args[0], args[1]
             pix = sum(arr[i].B * arr[i].H * arr[i].W for i in range(nl))
             tag = (1, pix, 1, arr[0].Cin, arr[0].Cout, arr[0].ksize)      # B*H*W folded into one factor

@@ -87,6 +87,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
                    tab['co'].data_ptr(), tab['nchunks'], _CHUNK, norm_sq.data_ptr())
         for (gi, group, plist), tab in zip(live, tabs):
             st0 = self.state[plist[0]]
+            # one bias correction per launch: every live parameter of the group must be at the same step (parameters
+            # that start receiving gradients later, or checkpoints with per-parameter counts, would silently get the
+            # wrong correction -- torch.optim.AdamW tracks the count per parameter)
+            steps = {int(self.state[p]['step']) for p in plist}
+            if len(steps) > 1:
+                raise N.EffdetNativeError('FusedClipAdamW: parameters of one group are at different steps %s; put late '
+                                          'starters into their own param group' % sorted(steps))
             step = int(st0['step']) + 1          # int() also accepts the tensor step of a torch.optim.AdamW checkpoint
             for p in plist:
                 self.state[p]['step'] = step

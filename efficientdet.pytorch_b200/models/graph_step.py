@@ -51,7 +51,12 @@ class GraphedTrainStep:
                 p.grad = None
         cl, rl = self.model([self.static_images, self.static_annots])
         loss = cl.mean() + rl.mean()
-        loss.backward()
+        # torch.autograd.grad, not .backward(): AccumulateGrad nodes remember the stream of an earlier eager step (the
+        # legacy stream if the caller still holds that step's loss) and would make it wait on the capturing stream --
+        # cudaErrorStreamCaptureImplicit.  The returned tensors live in the graph's pool: every replay rewrites them.
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        for p, g in zip(params, grads):
+            p.grad = g
         if self.optimizer is not None:
             self.optimizer.step()
         return loss.detach()

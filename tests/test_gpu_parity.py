@@ -348,6 +348,49 @@ def test_expand_gradients_from_bf16_planes(B, H, W, Cin, Cexp):
     assert _rel(dw.cpu(), wr.grad) < TOL_TC
 
 
+@pytest.mark.parametrize('B,H,W,Cin,Cout,mode', [
+    (2, 16, 16, 144, 24, 'project'), (1, 4, 4, 32, 16, 'project'), (3, 10, 10, 96, 24, 'project'),
+    (2, 8, 8, 1152, 192, 'project'), (2, 8, 8, 1152, 320, 'project'), (5, 9, 7, 240, 40, 'plain'),
+    (2, 32, 32, 16, 96, 'planes'), (3, 8, 8, 192, 1152, 'planes'), (1, 16, 16, 112, 672, 'plain'),
+    (2, 16, 16, 24, 144, 'plain'), (40, 32, 32, 40, 240, 'planes'), (1, 5, 3, 8, 8, 'plain'),
+])
+def test_pointwise_wgrad_fused_kernel(B, H, W, Cin, Cout, mode):
+    """pw_wgrad_kernel: weight gradient of a 1x1 conv straight from the fp32 tensors (converter warps apply the
+    BN+swish+SE-gate prologue and split to bf16 hi/lo in shared memory; GEMM-K = pixels) vs torch fp32 -- pixel tails
+    that are not a multiple of the 64-pixel stage, several input-channel tiles (Cin > 256), several output-channel
+    tiles (Cout > 128), dy given as fp32 or as bf16 planes, accumulation into a non-zero dw."""
+    ops = _ops()
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 77 + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5
+    sc, sh = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.3
+    gate = torch.rand(B, Cin, generator=g)
+    a = x
+    if mode == 'project':
+        a = _swish(x * sc[None, :, None, None] + sh[None, :, None, None]) * gate[:, :, None, None]
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(a, wr).backward(dy)
+    dw0 = torch.randn(Cout, Cin, 1, 1, generator=g)
+    dw = dw0.clone().to(dev)
+    xd, dyd = _nhwc(x), _nhwc(dy)
+    kw = {}
+    if mode == 'project':
+        kw = dict(a_scale=gate.to(dev), in_scale=sc.to(dev), in_shift=sh.to(dev))
+    if mode == 'planes':
+        hi = dyd.to(torch.bfloat16)
+        lo = (dyd - hi.float()).to(torch.bfloat16)
+        planes = torch.stack([hi, lo]).contiguous()
+        if not ops.planes_ok(B, H, W, Cout):
+            pytest.skip('no pixel-box geometry for the fallback contract')
+        ops.conv_wgrad_raw(xd, ops.N.f32(xd), H * W * Cin, None, H * W * Cout, dw, None, B, H, W, Cin, Cout, 1, tc=True,
+                           dy_planes=planes)
+    else:
+        ops.conv_wgrad(xd, dyd, dw, None, 1, tc=True, **kw)
+    assert _rel(dw.cpu() - dw0, wr.grad) < TOL_TC
+
+
 def test_layout_transposes():
     from models import _ops as ops
     x = torch.randn(3, 24, 7, 9)
