@@ -239,6 +239,12 @@ def run_ours(args):
     assert world == args.gpus, 'WORLD_SIZE=%d but --gpus %d (launch with torch.distributed.run)' % (world, args.gpus)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # N > 1: the DDP step (NCCL all-reduces included) is replayed as one CUDA graph too -- torch's recipe needs the
+    # watchdog's async error handling off before the process group exists (opt-in with EFFDET_DDP_GRAPH=1; default: eager DDP)
+    ddp_graph = train and world > 1 and not args.no_graph and os.environ.get('EFFDET_DDP_GRAPH', '0') == '1'
+    if ddp_graph:
+        os.environ['TORCH_NCCL_ASYNC_ERROR_HANDLING'] = '0'
+        os.environ['NCCL_ASYNC_ERROR_HANDLING'] = '0'
     if world > 1:
         import datetime
         dist.init_process_group(backend='nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -261,11 +267,15 @@ def run_ours(args):
         # unused parameters never changes, so static_graph lets DDP learn it once instead of searching the autograd
         # graph and synchronising a usage bitmap every iteration (EFFDET_DDP_STATIC=0 restores the per-step search)
         static = os.environ.get('EFFDET_DDP_STATIC', '1') != '0'
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
-                                                        static_graph=static, gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=float(os.environ.get('EFFDET_DDP_BUCKET_MB', '25')),
-                                                        # BN statistics are frozen (freeze_bn): nothing to re-broadcast per step
-                                                        broadcast_buffers=os.environ.get('EFFDET_DDP_BCAST', '0') == '1')
+        side = torch.cuda.Stream(device=dev)          # constructed on a side stream: DDP's AccumulateGrad hooks must not
+        side.wait_stream(torch.cuda.current_stream(dev))   # be tied to the legacy stream if the step is to be captured
+        with torch.cuda.stream(side):
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], find_unused_parameters=True,
+                                                            static_graph=static, gradient_as_bucket_view=True,
+                                                            bucket_cap_mb=float(os.environ.get('EFFDET_DDP_BUCKET_MB', '25')),
+                                                            # BN statistics are frozen (freeze_bn): nothing to re-broadcast per step
+                                                            broadcast_buffers=os.environ.get('EFFDET_DDP_BCAST', '0') == '1')
+        torch.cuda.current_stream(dev).wait_stream(side)
 
     images_h, ann_h = synthetic(cfgd, BS, seed=1000 + rank)
     images_h, ann_h = images_h.pin_memory(), ann_h.pin_memory()
@@ -307,18 +317,23 @@ def run_ours(args):
             ms = float(t)
         return ms
 
-    for _ in range(args.warmup):
-        step(images_d, ann_d)
+    if not ddp_graph:                  # (the DDP graph path warms up on GraphedTrainStep's side stream instead)
+        for _ in range(args.warmup):
+            step(images_d, ann_d)
     # single-GPU training configs replay the step as ONE CUDA graph (models/graph_step.py: the public helper a user
     # of the drop-in would call): ~480 launches cost the host one cudaGraphLaunch instead of 12-16 ms of Python
     graphed, graph_note, graph_launches = None, 'eager', None
-    if train and world == 1 and not args.no_graph:
+    if train and not args.no_graph and (world == 1 or ddp_graph):
         try:
             from models.graph_step import GraphedTrainStep
-            _native.reset_launch_count()
-            graphed = GraphedTrainStep(model, images_d, ann_d, warmup=0)
-            graph_launches = _native.launch_count()          # kernels of this library recorded into the graph
-            graph_note = 'cuda graph (GraphedTrainStep), %d library kernels per replay' % graph_launches
+            if ddp_graph:
+                graphed = GraphedTrainStep(net, images_d, ann_d, warmup=max(11, args.warmup))
+                graph_launches = graphed.library_launches
+                graph_note = 'cuda graph incl. the NCCL all-reduces (GraphedTrainStep over DDP), %d library kernels per replay' % graph_launches
+            else:
+                graphed = GraphedTrainStep(model, images_d, ann_d, warmup=0)
+                graph_launches = graphed.library_launches        # kernels of this library recorded into the graph
+                graph_note = 'cuda graph (GraphedTrainStep), %d library kernels per replay' % graph_launches
             eager_step = step
 
             def step(x, a, module=None):                     # noqa: F811
@@ -451,8 +466,16 @@ def run_ours(args):
                     gpu_launches=launches, host_issue_ms_per_step=round(host_ms, 2), roofline=roofline, cpu_baseline=cpu_base, kernel_breakdown=breakdown,
                     kernel_rooflines=kroof if args.full_breakdown else None,
                     model_tflops=round((3 if train else 1) * cfgd['fwd_gflop'] * imgs / (ms * 1e-3) / 1e3, 2))
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        if graphed is not None:
+            # with a live CUDA graph that holds NCCL kernels the teardown (graph / communicator destructors) waits
+            # forever on this stack (seen on 2 x B200): the result is out, leave without it
+            torch.cuda.synchronize()
+            dist.barrier(device_ids=[local])
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

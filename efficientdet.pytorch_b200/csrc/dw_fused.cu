@@ -197,11 +197,22 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
     const bool cv_ok = cv < cvecs;
     const int b = blockIdx.z;
     const int cq = cv_ok ? cv * 4 : 0;
-    const float4 sc1 = ldg4(p.scale1 + cq), sh1 = ldg4(p.shift1 + cq), mu1 = ldg4(p.mean1 + cq), rs1 = ldg4(p.rstd1 + cq);
-    float4 sc0 = f4zero(), sh0 = f4zero(), mu0 = f4zero(), rs0 = f4zero();
-    if (PRE) { sc0 = ldg4(p.scale0 + cq); sh0 = ldg4(p.shift0 + cq); mu0 = ldg4(p.mean0 + cq); rs0 = ldg4(p.rstd0 + cq); }
-    const float4 gt = ldg4(p.gate + (long long)b * p.C + cq);
-    const float4 dm = f4scale(ldg4(p.dmean + (long long)b * p.C + cq), p.inv_hw);
+    // per-channel constants live in shared memory, not in 40 registers: the 5x5 kernels already carry 25 float4
+    // weight-gradient accumulators per thread and spilled them when these stayed in registers
+    float4* cst = red + NQ * (kDwT / 32) * kCVc;         // [10][kCVc]: sc1 sh1 mu1 rs1 gate dmean/HW sc0 sh0 mu0 rs0
+    if (t < 10 * kCVc) {
+        const int q = t >> 2, c4 = (blockIdx.x * kCVc + (t & 3)) * 4;
+        float4 v = f4zero();
+        if (c4 < p.C) {
+            const float* src = q == 0 ? p.scale1 : q == 1 ? p.shift1 : q == 2 ? p.mean1 : q == 3 ? p.rstd1
+                             : q == 4 ? p.gate + (long long)b * p.C : q == 5 ? p.dmean + (long long)b * p.C
+                             : q == 6 ? p.scale0 : q == 7 ? p.shift0 : q == 8 ? p.mean0 : p.rstd0;
+            if (q < 6 || PRE) v = ldg4(src + c4);
+            if (q == 5) v = f4scale(v, p.inv_hw);
+        }
+        cst[t] = v;
+    }
+#define DWC(q_) cst[(q_) * kCVc + cvl]
     for (int i = t; i < KK * kCVc; i += kDwT) ws[i] = cv_ok ? ldg4(p.w_kkc + (long long)(i >> 2) * p.C + cq) : f4zero();
     const float* dqb = p.dq + (long long)b * p.Ho * p.Wo * p.C + cq;
     const float* z1b = p.z1 + (long long)b * p.Ho * p.Wo * p.C + cq;
@@ -243,12 +254,13 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
             const int r = pix / G::GW, c = pix - r * G::GW;
             const int oy = cy0 + r + G::DMIN, ox = cx0 + c + G::DMIN;
             if (!(cv_ok && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo)) continue;     // zero-filled: contributes nothing
-            const float4 g = f4fma(gs[pix * kPS + cvl], gt, dm);              // SE product rule: d(a1*gate) + d(mean)
+            const float4 g = f4fma(gs[pix * kPS + cvl], DWC(4), DWC(5));              // SE product rule: d(a1*gate) + d(mean)
             const float4 z = z1s[pix * kPS + cvl];
-            const float4 du = f4mul(g, f4swish_grad(f4fma(z, sc1, sh1)));
+            const float4 sc1 = DWC(0);
+            const float4 du = f4mul(g, f4swish_grad(f4fma(z, sc1, DWC(1))));
             const bool owned = r + G::DMIN >= 0 && r + G::DMIN < G::TCY && c + G::DMIN >= 0 && c + G::DMIN < G::TCX;
             if (owned) {                                                       // each output is counted by exactly one tile
-                sg1 = f4fma(du, f4mul(f4sub(z, mu1), rs1), sg1);
+                sg1 = f4fma(du, f4mul(f4sub(z, DWC(2)), DWC(3)), sg1);
                 sb1 = f4add(sb1, du);
             }
             gs[pix * kPS + cvl] = f4mul(du, sc1);
@@ -262,7 +274,7 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
                 const bool ok = cv_ok && iy < p.H && ix < p.W;
                 float4 sg = f4zero();                       // sigmoid(bn0(z0)): a0 = u*sg and swish'(u) both follow from it
                 if (ok) {
-                    const float4 q = f4fma(zs[pix * kPS + cvl], sc0, sh0);
+                    const float4 q = f4fma(zs[pix * kPS + cvl], DWC(6), DWC(7));
                     sg = make_float4(fsigmoid(q.x), fsigmoid(q.y), fsigmoid(q.z), fsigmoid(q.w));
                 }
                 as[pix * kPS + cvl] = sg;
@@ -285,7 +297,7 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
                         da[i] = f4zero();
                         a0[i] = as[(arow + i * S) * kPS + cvl];
                         if (PRE)                              // staged: sigmoid(u) and raw z0 -> a0 = u * sigmoid(u)
-                            a0[i] = f4mul(f4fma(zs[(arow + i * S) * kPS + cvl], sc0, sh0), a0[i]);   // out of image: sigmoid staged as 0
+                            a0[i] = f4mul(f4fma(zs[(arow + i * S) * kPS + cvl], DWC(6), DWC(7)), a0[i]);   // out of image: sigmoid staged as 0
                     }
 #pragma unroll
                     for (int ky = 0; ky < K; ++ky) {
@@ -317,11 +329,12 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
                         float4 out = da[i];
                         if (PRE) {
                             const float4 z = zs[(arow + i * S) * kPS + cvl];
-                            const float4 sg = as[(arow + i * S) * kPS + cvl], uu = f4fma(z, sc0, sh0);   // swish'(u) = s * (1 + u * (1 - s))
+                            const float4 sc0 = DWC(6);
+                            const float4 sg = as[(arow + i * S) * kPS + cvl], uu = f4fma(z, sc0, DWC(7));   // swish'(u) = s * (1 + u * (1 - s))
                             const float4 sp = make_float4(sg.x * (1.f + uu.x * (1.f - sg.x)), sg.y * (1.f + uu.y * (1.f - sg.y)),
                                                           sg.z * (1.f + uu.z * (1.f - sg.z)), sg.w * (1.f + uu.w * (1.f - sg.w)));
                             const float4 du = f4mul(da[i], sp);
-                            sg0 = f4fma(du, f4mul(f4sub(z, mu0), rs0), sg0);
+                            sg0 = f4fma(du, f4mul(f4sub(z, DWC(8)), DWC(9)), sg0);
                             sb0 = f4add(sb0, du);
                             out = f4mul(du, sc0);
                         }
@@ -372,6 +385,8 @@ dw_bwd_fused_kernel(const effdet_dw_bwd_args p, const int tiles_x, const int nti
     }
 }
 
+#undef DWC
+
 template <int K, int S, bool PRE, bool SMALL>
 static size_t dw_fwd_smem() {
     using G = DwGeo<K, S, SMALL>;
@@ -383,7 +398,7 @@ static size_t dw_bwd_smem() {
     using G = DwGeo<K, S, SMALL>;
     constexpr int kDwT = G::NT;
     return (size_t)(2 * G::GH * G::GW * kPS + (PRE ? 2 : 1) * G::BIH * G::BIW * kPS + K * K * kCVc +
-                    (K * K + 4) * (kDwT / 32) * kCVc) * sizeof(float4);
+                    (K * K + 4) * (kDwT / 32) * kCVc + 10 * kCVc) * sizeof(float4);
 }
 
 // tiles per CTA: keep >= ~6 waves of CTAs in the grid, but let a CTA amortise its reductions over up to 8 tiles

@@ -16,10 +16,11 @@
 
 namespace effdet {
 
-constexpr int kWgConv = 12;                     // converter warps (12 * 32 threads * ~150 registers: room for the double-buffered loads)
+constexpr int kWgConv = 8;                      // converter warps: few, with ~220 registers each -- a spilled variable shares its
+                                                // scoreboard with the prefetched loads and would wait for them (measured: 68 % long-scoreboard stalls)
 constexpr int kWgCT = kWgConv * 32;             // converter threads
 constexpr int kWgThreads = kWgCT + 32;          // + the MMA warp
-constexpr int kWgUnits = 4;                     // 8-channel units per converter thread and stage: K * (octs of x + dy) <= 1536
+constexpr int kWgUnits = 6;                     // 8-channel units per converter thread and stage: K * (octs of x + dy) <= 1536
 
 struct PwWgParams {
     const float* x;
@@ -30,8 +31,8 @@ struct PwWgParams {
     const float* a_scale;
     float* dw;
     int M, HW, Cin, Cout;
-    int ntn, NX, TM;                // input-channel tiles, their width (multiple of 16, <= 128), output channels per tile (<= 128)
-    int K;                          // pixels per stage: 64, or 128 for narrow tiles (more bytes in flight per thread)
+    int ntn, NX, TM;                // input-channel tiles, their width (multiple of 16, <= 256), output channels per tile (<= 128)
+    int K;                          // pixels per stage: 32 / 64 / 128, the largest with K * (channel octets) <= 1536
     int nchunks, cps;               // K-pixel chunks, chunks per split
     int NS, stage_bytes;            // ring depth, bytes per stage
     int a_plane, b_plane;           // bytes of one dy / x plane of a stage (1 or 2 groups of 64 channels)
@@ -41,9 +42,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_constant__ PwWgParams P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-byte aligned, still a shared pointer
     uint8_t* ctl = smem + P.NS * P.stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctl);
     uint64_t* empty_bar = full_bar + 4;
@@ -69,11 +74,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_co
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == kWgConv) tmem_alloc<128>(tmem_slot);
+    if (warp == kWgConv) tmem_alloc<256>(tmem_slot);
     if (P.in_scale)
         for (int i = threadIdx.x; i < ncur; i += kWgThreads) {
             chan[i] = __ldg(P.in_scale + c0 + i);
-            chan[128 + i] = __ldg(P.in_shift + c0 + i);
+            chan[256 + i] = __ldg(P.in_shift + c0 + i);
         }
     tc_fence_before();
     __syncthreads();
@@ -81,84 +86,104 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < kWgConv) {
-        // this thread's units: the same (pixel row, channel octet) of every stage.  kind 0 = x, 1 = dy, 2 = none
+        // This thread's units: the same (pixel row, channel octet) of every chunk; unit i is an x unit (bit i of xmask),
+        // a dy unit (bit i of ymask) or nothing.  Everything that changes from chunk to chunk is advanced by additions.
         const int nxo = ncur >> 3, nyo = mcur >> 3;
         const int UX = P.K * nxo, U = UX + P.K * nyo;
         const bool planes = P.dy_planes != nullptr;
-        int kind[kWgUnits], prow[kWgUnits], ooff[kWgUnits];
-        const char* src[kWgUnits];
-        uint32_t dst[kWgUnits];
-        size_t step_x = (size_t)P.K * P.Cin * 4, step_y = (size_t)P.K * P.Cout * (planes ? 2 : 4);
+        const uint32_t smem_a = smem_u32(smem);
+        uint32_t xmask = 0, ymask = 0;
+        const char* src[kWgUnits];          // first 16 bytes of the unit in chunk kt (advanced every load)
+        uint32_t dst[kWgUnits];             // shared address of the hi half in stage 0
+        int pix[kWgUnits];                  // global pixel of the unit in the chunk being LOADED
+        int cof[kWgUnits];                  // x units: channel offset inside the tile
+        const float* gate[kWgUnits];        // x units: a_scale row of the image the CONVERTED pixel belongs to
+        int rem[kWgUnits];                  //          ... and the pixel's index inside that image
 #pragma unroll
         for (int i = 0; i < kWgUnits; ++i) {
             const int u = threadIdx.x + i * kWgCT;
-            kind[i] = 2; prow[i] = 0; ooff[i] = 0; src[i] = nullptr; dst[i] = 0;
+            src[i] = nullptr; dst[i] = 0; pix[i] = 0; cof[i] = 0; gate[i] = nullptr; rem[i] = 0;
             if (u < UX) {
                 const int p = u / nxo, o = u - p * nxo;
-                kind[i] = 0; prow[i] = p; ooff[i] = o * 8;
-                src[i] = reinterpret_cast<const char*>(P.x + ((size_t)ch_begin * P.K + p) * P.Cin + c0 + o * 8);
-                dst[i] = 2 * P.a_plane + (o >> 3) * group + p * 128 + (((o & 7) ^ (p & 7)) << 4);
+                xmask |= 1u << i;
+                pix[i] = ch_begin * P.K + p;
+                cof[i] = o * 8;
+                src[i] = reinterpret_cast<const char*>(P.x + (size_t)pix[i] * P.Cin + c0 + o * 8);
+                dst[i] = smem_a + 2 * P.a_plane + (o >> 3) * group + p * 128 + (((o & 7) ^ (p & 7)) << 4);
+                if (P.a_scale) {
+                    const int b = pix[i] / P.HW;
+                    rem[i] = pix[i] - b * P.HW;
+                    gate[i] = P.a_scale + (size_t)b * P.Cin + c0 + o * 8;
+                }
             } else if (u < U) {
                 const int v = u - UX;
                 const int p = v / nyo, o = v - p * nyo;
-                kind[i] = 1; prow[i] = p;
-                const size_t e = ((size_t)ch_begin * P.K + p) * P.Cout + n0 + o * 8;
+                ymask |= 1u << i;
+                pix[i] = ch_begin * P.K + p;
+                const size_t e = (size_t)pix[i] * P.Cout + n0 + o * 8;
                 src[i] = planes ? reinterpret_cast<const char*>(P.dy_planes + e) : reinterpret_cast<const char*>(P.dy + e);
-                dst[i] = (o >> 3) * group + p * 128 + (((o & 7) ^ (p & 7)) << 4);
+                dst[i] = smem_a + (o >> 3) * group + p * 128 + (((o & 7) ^ (p & 7)) << 4);
             }
         }
-        const size_t plane_bytes = (size_t)P.M * P.Cout * 2;    // hi -> lo plane of dy
+        const size_t step_x = (size_t)P.K * P.Cin * 4, step_y = (size_t)P.K * P.Cout * (planes ? 2 : 4);
+        const size_t second_y = planes ? (size_t)P.M * P.Cout * 2 : 16;       // hi -> lo plane of dy, or the next 4 floats
+        const bool have_in = P.in_scale != nullptr, have_gate = P.a_scale != nullptr;
         float4 va[2][kWgUnits], vb[2][kWgUnits];
-        auto load = [&](int kt, float4 (&a)[kWgUnits], float4 (&b)[kWgUnits]) {
-            const int m0 = (ch_begin + kt) * P.K;
+        uint32_t okmask[2] = {0, 0};                                          // units of the buffered chunk inside the tensor
+        auto load = [&](float4 (&a)[kWgUnits], float4 (&b)[kWgUnits], uint32_t& ok) {
+            ok = 0;
 #pragma unroll
             for (int i = 0; i < kWgUnits; ++i) {
                 a[i] = b[i] = f4zero();
-                if (kind[i] != 2 && m0 + prow[i] < P.M) {
-                    const char* s = src[i] + (size_t)kt * (kind[i] == 0 ? step_x : step_y);
-                    a[i] = __ldg(reinterpret_cast<const float4*>(s));
-                    b[i] = __ldg(reinterpret_cast<const float4*>(s + ((kind[i] == 1 && planes) ? plane_bytes : 16)));
+                const bool isx = (xmask >> i) & 1, isy = (ymask >> i) & 1;
+                if ((isx || isy) && pix[i] < P.M) {
+                    ok |= 1u << i;
+                    a[i] = __ldg(reinterpret_cast<const float4*>(src[i]));
+                    b[i] = __ldg(reinterpret_cast<const float4*>(src[i] + (isx ? (size_t)16 : second_y)));
                 }
+                src[i] += isx ? step_x : step_y;
+                pix[i] += P.K;
             }
         };
-        auto convert = [&](int kt, float4 (&a)[kWgUnits], float4 (&b)[kWgUnits]) {
+        auto convert = [&](int kt, float4 (&a)[kWgUnits], float4 (&b)[kWgUnits], const uint32_t ok) {
             const int s = kt % P.NS;
-            const int m0 = (ch_begin + kt) * P.K;
             if (lane == 0) mbar_wait(&empty_bar[s], ((kt / P.NS) & 1) ^ 1);   // the MMAs that last read the slot are done
             __syncwarp();
-            uint8_t* st = smem + (size_t)s * P.stage_bytes;
+            const uint32_t so = (uint32_t)s * (uint32_t)P.stage_bytes;
 #pragma unroll
             for (int i = 0; i < kWgUnits; ++i) {
-                if (kind[i] == 2) continue;
                 uint4 hi, lo;
-                if (kind[i] == 0) {
+                if ((xmask >> i) & 1) {
                     float4 xa = a[i], xb = b[i];
-                    if (m0 + prow[i] < P.M) {
-                        if (P.in_scale) {
-                            const float* cs = chan + ooff[i];
-                            xa = f4fma(xa, *reinterpret_cast<const float4*>(cs), *reinterpret_cast<const float4*>(cs + 128));
-                            xb = f4fma(xb, *reinterpret_cast<const float4*>(cs + 4), *reinterpret_cast<const float4*>(cs + 132));
+                    if ((ok >> i) & 1) {
+                        if (have_in) {
+                            const float* cs = chan + cof[i];
+                            xa = f4fma(xa, *reinterpret_cast<const float4*>(cs), *reinterpret_cast<const float4*>(cs + 256));
+                            xb = f4fma(xb, *reinterpret_cast<const float4*>(cs + 4), *reinterpret_cast<const float4*>(cs + 260));
                             xa = make_float4(fswish(xa.x), fswish(xa.y), fswish(xa.z), fswish(xa.w));
                             xb = make_float4(fswish(xb.x), fswish(xb.y), fswish(xb.z), fswish(xb.w));
                         }
-                        if (P.a_scale) {
-                            const float* g = P.a_scale + (size_t)((m0 + prow[i]) / P.HW) * P.Cin + c0 + ooff[i];
-                            xa = f4mul(xa, ldg4(g));
-                            xb = f4mul(xb, ldg4(g + 4));
+                        if (have_gate) {
+                            xa = f4mul(xa, ldg4(gate[i]));
+                            xb = f4mul(xb, ldg4(gate[i] + 4));
                         }
                     }
+                    if (have_gate) {                                          // move on to the pixel of the next chunk
+                        rem[i] += P.K;
+                        while (rem[i] >= P.HW) { rem[i] -= P.HW; gate[i] += P.Cin; }
+                    }
                     split8(xa, xb, hi, lo);
-                    *reinterpret_cast<uint4*>(st + dst[i]) = hi;
-                    *reinterpret_cast<uint4*>(st + dst[i] + P.b_plane) = lo;
-                } else {
+                    sts128(dst[i] + so, hi);
+                    sts128(dst[i] + so + P.b_plane, lo);
+                } else if ((ymask >> i) & 1) {
                     if (planes) {
                         hi = *reinterpret_cast<const uint4*>(&a[i]);
                         lo = *reinterpret_cast<const uint4*>(&b[i]);
                     } else {
                         split8(a[i], b[i], hi, lo);
                     }
-                    *reinterpret_cast<uint4*>(st + dst[i]) = hi;
-                    *reinterpret_cast<uint4*>(st + dst[i] + P.a_plane) = lo;
+                    sts128(dst[i] + so, hi);
+                    sts128(dst[i] + so + P.a_plane, lo);
                 }
             }
             fence_proxy_async();
@@ -166,16 +191,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_co
             if (lane == 0) mbar_arrive(&full_bar[s]);
         };
         // software pipeline: the loads of chunk kt+1 are in flight while chunk kt is converted
-        load(0, va[0], vb[0]);
+        load(va[0], vb[0], okmask[0]);
         for (int kt = 0; kt < KT; kt += 2) {
-            if (kt + 1 < KT) load(kt + 1, va[1], vb[1]);
-            convert(kt, va[0], vb[0]);
+            if (kt + 1 < KT) load(va[1], vb[1], okmask[1]);
+            convert(kt, va[0], vb[0], okmask[0]);
             if (kt + 1 < KT) {
-                if (kt + 2 < KT) load(kt + 2, va[0], vb[0]);
-                convert(kt + 1, va[1], vb[1]);
+                if (kt + 2 < KT) load(va[0], vb[0], okmask[0]);
+                convert(kt + 1, va[1], vb[1], okmask[1]);
             }
         }
-        // epilogue: TMEM lane = output channel, column = input channel; warp w drains lane quarter w % 4, column groups w / 4, w / 4 + 3
+        // epilogue: TMEM lane = output channel, column = input channel; warp w drains lane quarter w % 4, column groups w / 4, w / 4 + 2, ...
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int quarter = warp & 3;
@@ -224,7 +249,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_co
     __syncthreads();
     if (warp == kWgConv) {
         tc_fence_after();
-        tmem_dealloc<128>(tmem_base);
+        tmem_dealloc<256>(tmem_base);
     }
 }
 
@@ -260,26 +285,17 @@ int pw_wgrad_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     P.M = a->B * P.HW;
     P.Cin = a->Cin;
     P.Cout = a->Cout;
-    // balanced tiles, (x, dy) channels per tile <= (128, 64) or (64, 128) -- whichever re-reads fewer bytes: every
-    // output-channel tile reads x again, every input-channel tile reads dy again
-    int best = -1;
-    long long best_cost = 0;
-    for (int opt = 0; opt < 2; ++opt) {
-        const int nx_max = opt ? 64 : 128, tm_max = opt ? 128 : 64;
-        const int ntn = cdiv(a->Cin, nx_max), ntm = cdiv(a->Cout, tm_max);
-        const long long cost = (long long)ntm * a->Cin + (long long)ntn * a->Cout;
-        if (best < 0 || cost < best_cost) { best = opt; best_cost = cost; }
-    }
-    const int nx_max = best ? 64 : 128, tm_max = best ? 128 : 64;
-    P.ntn = cdiv(a->Cin, nx_max);
+    // balanced tiles: input channels in pieces of <= 256 (multiple of 16), output channels in pieces of <= 128 (multiple
+    // of 8).  Every output-channel tile reads x again, every input-channel tile reads dy again -- wide tiles keep that small.
+    P.ntn = cdiv(a->Cin, 256);
     P.NX = cdiv(cdiv(a->Cin, P.ntn), 16) * 16;
     P.ntn = cdiv(a->Cin, P.NX);
-    int ntm = cdiv(a->Cout, tm_max);
+    int ntm = cdiv(a->Cout, 128);
     P.TM = cdiv(cdiv(a->Cout, ntm), 8) * 8;
     ntm = cdiv(a->Cout, P.TM);
     const int tiles = P.ntn * ntm;
     const int octs = (P.NX < a->Cin ? P.NX : a->Cin) / 8 + P.TM / 8;
-    P.K = octs <= 12 ? 128 : 64;                                 // K * octs <= 1536 units = 4 per converter thread
+    P.K = octs <= 12 ? 128 : (octs <= 24 ? 64 : 32);             // K * octs <= 1536 units = 6 per converter thread
     P.nchunks = cdiv(P.M, P.K);
     int splits = 148 / tiles;
     if (splits < 1) splits = 1;
@@ -292,7 +308,7 @@ int pw_wgrad_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     P.stage_bytes = 2 * P.a_plane + 2 * P.b_plane;
     P.NS = (200 * 1024) / P.stage_bytes;
     if (P.NS > 4) P.NS = 4;
-    const size_t smem = (size_t)P.NS * P.stage_bytes + 128 + 2 * 128 * sizeof(float) + 1024;
+    const size_t smem = (size_t)P.NS * P.stage_bytes + 128 + 2 * 256 * sizeof(float) + 1024;
     cudaError_t e = cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(pw): smem opt-in: %s", cudaGetErrorString(e));
     pw_wgrad_kernel<<<dim3(tiles, splits), kWgThreads, smem, st>>>(P);

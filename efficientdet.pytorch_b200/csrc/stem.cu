@@ -105,72 +105,82 @@ __global__ void __launch_bounds__(128) stem_fwd_px_kernel(const float* __restric
     }
 }
 
-constexpr int kStemP = 64;     // pixels staged per iteration
-constexpr int kStemMaxT = 2;   // taps per thread upper bound: 27 <= 2 * (256 / (C0/4)) for C0 <= 72
+constexpr int kStemP = 64;     // output pixels (one row segment) per work unit
 
-// dw[co][tap] += sum_pixels x[pixel + tap] * dz[pixel][co]  -- a 27 x C0 GEMM over ~2 M pixels, shared-memory bound:
-// a thread owns 4 output channels (one 128-bit shared load of dz per pixel) and 1-2 taps (32-bit broadcast loads of
-// the im2col row), i.e. 4 FMAs per 2 shared loads; the previous mapping (1 channel x 4 taps) paid 2 loads per FMA
-// and ran at 0.07 of the HBM roofline.
+// dw[co][tap] += sum_pixels x[pixel + tap] * dz[pixel][co]  -- a 27 x C0 GEMM over ~2 M pixels.  A work unit is a
+// 64-pixel segment of one output row: the 3 x 3 input row segments it touches (129 floats each, read coalesced from
+// the NCHW image) and the 64 x C0 slice of dz are staged in shared memory; a warp owns 8 of the pixels, a lane owns 4
+// output channels x TPG taps (C0 = 32: 8 channel vectors x 4 tap groups of 7), i.e. per pixel one 128-bit load of dz
+// and TPG broadcast loads of x feed 4*TPG FMAs -- FMA-bound instead of shared-memory-bound (the previous mapping
+// issued 2 shared loads per 4 FMAs and sat at 0.09 of the HBM roofline).
+template <int TPG>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                          float* __restrict__ dw, int B, int H, int W, int C0, int Ho,
-                                                         int Wo) {
+                                                         int Wo, int segs, long long units) {
     extern __shared__ __align__(16) float sm[];
-    float* xs = sm;                    // [kStemP][28]  (27 taps, padded)
-    float* ds = sm + kStemP * 28;      // [kStemP][C0]
-    const int t = threadIdx.x;
-    const int cvs = C0 / 4;            // channel vectors
-    const int ntg = 256 / cvs;         // tap groups
-    const int cv = t % cvs, tg = t / cvs;
-    const bool worker = tg < ntg;
-    float4 acc[kStemMaxT];
+    float* xr = sm;                    // [9][132]: (ci, ky) row segments, columns 2*ox0 .. 2*ox0 + 128
+    float* ds = sm + 9 * 132;          // [kStemP][C0]; reused for the cross-warp reduction
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int cvs = C0 / 4, tgs = 32 / cvs;
+    const int cv = lane % cvs, tg = lane / cvs;
+    const bool worker = tg < tgs;
+    int off[TPG];                      // shared-memory offset of this lane's taps (pixel 0); -1 = no tap
 #pragma unroll
-    for (int j = 0; j < kStemMaxT; ++j) acc[j] = f4zero();
-    const long long npix = (long long)B * Ho * Wo;
-    for (long long p0 = (long long)blockIdx.x * kStemP; p0 < npix; p0 += (long long)gridDim.x * kStemP) {
-        for (int i = t; i < kStemP * 27; i += 256) {
-            const int pp = i / 27, tap = i - pp * 27;
-            const long long pix = p0 + pp;
-            float v = 0.f;
-            if (pix < npix) {
-                const int ox = (int)(pix % Wo);
-                const long long r = pix / Wo;
-                const int oy = (int)(r % Ho);
-                const int b = (int)(r / Ho);
-                const int ci = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
-                const int iy = 2 * oy + ky, ix = 2 * ox + kx;
-                if (iy < H && ix < W) v = __ldg(x + (((long long)b * 3 + ci) * H + iy) * W + ix);
-            }
-            xs[pp * 28 + tap] = v;
+    for (int j = 0; j < TPG; ++j) {
+        const int tap = tg * TPG + j;
+        off[j] = (worker && tap < 27) ? (tap / 3) * 132 + tap % 3 : -1;
+    }
+    float4 acc[TPG];
+#pragma unroll
+    for (int j = 0; j < TPG; ++j) acc[j] = f4zero();
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int seg = (int)(u % segs);
+        const long long r = u / segs;
+        const int oy = (int)(r % Ho), b = (int)(r / Ho);
+        const int ox0 = seg * kStemP;
+        const int npx = min(kStemP, Wo - ox0);
+        __syncthreads();                                   // the previous unit has been consumed
+        for (int i = t; i < 9 * 132; i += 256) {
+            const int row = i / 132, c = i - row * 132;
+            const int ci = row / 3, ky = row - ci * 3;
+            const int iy = 2 * oy + ky, ix = 2 * ox0 + c;
+            xr[i] = (c <= 2 * kStemP && iy < H && ix < W) ? __ldg(x + (((long long)b * 3 + ci) * H + iy) * W + ix) : 0.f;
         }
-        for (int i = t; i < kStemP * C0 / 4; i += 256) {
-            const int pp = i / (C0 / 4), c4 = i - pp * (C0 / 4);
-            const long long pix = p0 + pp;
-            float4 v = f4zero();
-            if (pix < npix) v = ldg4(dz + pix * C0 + c4 * 4);
-            *reinterpret_cast<float4*>(&ds[pp * C0 + c4 * 4]) = v;
+        const float* dzr = dz + (((long long)b * Ho + oy) * Wo + ox0) * C0;
+        for (int i = t; i < kStemP * cvs; i += 256) {
+            const int pp = i / cvs;
+            *reinterpret_cast<float4*>(&ds[i * 4]) = pp < npx ? ldg4(dzr + (long long)i * 4) : f4zero();
         }
         __syncthreads();
         if (worker) {
-#pragma unroll 8
-            for (int pp = 0; pp < kStemP; ++pp) {
+#pragma unroll
+            for (int q = 0; q < kStemP / 8; ++q) {
+                const int pp = warp + q * 8;
                 const float4 g = *reinterpret_cast<const float4*>(&ds[pp * C0 + cv * 4]);
 #pragma unroll
-                for (int j = 0; j < kStemMaxT; ++j) {
-                    const int tap = tg + j * ntg;
-                    if (tap < 27) acc[j] = f4fma(make_float4(xs[pp * 28 + tap], xs[pp * 28 + tap], xs[pp * 28 + tap], xs[pp * 28 + tap]), g, acc[j]);
+                for (int j = 0; j < TPG; ++j) {
+                    if (off[j] < 0) continue;
+                    const float v = xr[off[j] + 2 * pp];
+                    acc[j] = f4fma(make_float4(v, v, v, v), g, acc[j]);
                 }
             }
         }
-        __syncthreads();
     }
-    if (worker) {
+    // cross-warp sum through shared memory, then one atomic per (channel, tap) and CTA
+    __syncthreads();
+    float4* red = reinterpret_cast<float4*>(ds);           // [8 warps][32 lanes], one tap slot at a time
+    for (int j = 0; j < TPG; ++j) {
+        __syncthreads();
+        red[warp * 32 + lane] = acc[j];
+        __syncthreads();
+        if (warp == 0 && worker) {
+            float4 s = red[lane];
 #pragma unroll
-        for (int j = 0; j < kStemMaxT; ++j) {
-            const int tap = tg + j * ntg;
+            for (int w = 1; w < 8; ++w) s = f4add(s, red[w * 32 + lane]);
+            const int tap = tg * TPG + j;
             if (tap < 27) {
                 float* o = dw + (cv * 4) * 27 + tap;
-                atomicAdd(o, acc[j].x); atomicAdd(o + 27, acc[j].y); atomicAdd(o + 54, acc[j].z); atomicAdd(o + 81, acc[j].w);
+                atomicAdd(o, s.x); atomicAdd(o + 27, s.y); atomicAdd(o + 54, s.z); atomicAdd(o + 81, s.w);
             }
         }
     }
@@ -212,10 +222,16 @@ extern "C" int effdet_stem_wgrad(const float* x_nchw, const float* dz, float* dw
     EFFDET_REQUIRE(aligned16(dz), "stem_wgrad: alignment");
     EFFDET_DEVICE(device);
     const int Ho = (H + 1 - 3) / 2 + 1, Wo = (W + 1 - 3) / 2 + 1;
-    const long long npix = (long long)B * Ho * Wo;
-    int blocks = cdiv(npix, kStemP);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    const size_t smem = (size_t)kStemP * (28 + C0) * sizeof(float);
-    stem_wgrad_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo);
+    const int segs = cdiv(Wo, kStemP);
+    const long long units = (long long)B * Ho * segs;
+    int blocks = (int)(units < 148 * 8 ? units : 148 * 8);
+    size_t smem = (size_t)(9 * 132 + kStemP * C0) * sizeof(float);
+    const size_t need = (size_t)(9 * 132) * sizeof(float) + 256 * sizeof(float4);     // cross-warp reduction scratch
+    if (smem < need) smem = need;
+    const int cvs = C0 / 4, tgs = 32 / cvs, tpg = cdiv(27, tgs);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tpg <= 7) stem_wgrad_kernel<7><<<blocks, 256, smem, st>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo, segs, units);
+    else if (tpg <= 9) stem_wgrad_kernel<9><<<blocks, 256, smem, st>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo, segs, units);
+    else stem_wgrad_kernel<14><<<blocks, 256, smem, st>>>(x_nchw, dz, dw_oihw, B, H, W, C0, Ho, Wo, segs, units);
     return launch_status("stem_wgrad_kernel");
 }

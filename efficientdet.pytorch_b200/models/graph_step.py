@@ -9,6 +9,10 @@ one cudaGraphLaunch, which matters as soon as the GPU finishes a step faster tha
     loss = step(images, annotations)      # copies into the static inputs, replays, returns the static loss tensor
     ... model parameters' .grad now hold this step's gradients (same tensors every step)
 
+Build it BEFORE any eager step, or after every reference to earlier eager losses / outputs has been dropped: a live autograd
+graph keeps the parameters' gradient accumulators bound to the stream it ran on (the legacy stream), and the engine
+may not touch that stream while another one is capturing.
+
 Shapes are static (the reference pads every batch to the common size and a fixed annotation count per batch can be
 obtained by padding with -1 rows, which FocalLoss ignores).  Drop-connect keeps working: torch.rand inside a captured
 region advances the Philox offset on every replay.  With `optimizer=FusedClipAdamW(...)` the clip + AdamW launches are
@@ -21,9 +25,17 @@ from . import _ops
 
 
 class GraphedTrainStep:
+    """model: the EfficientDet module, or its DistributedDataParallel wrapper.  For DDP the NCCL gradient all-reduces are
+    captured with the step (torch's documented recipe: NCCL >= 2.9.6, TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before
+    init_process_group, the DDP wrapper CONSTRUCTED inside a side-stream context, >= 11 eager warm-up iterations);
+    gradients then have to flow through DDP's AccumulateGrad hooks, so the captured step calls loss.backward()."""
+
     def __init__(self, model, images, annotations, optimizer=None, warmup=3):
         if not images.is_cuda:
             raise _ops.N.EffdetNativeError('GraphedTrainStep needs CUDA example inputs')
+        self.ddp = isinstance(model, torch.nn.parallel.DistributedDataParallel)
+        if self.ddp:
+            warmup = max(warmup, 11)
         self.model = model
         self.optimizer = optimizer
         self.static_images = images.clone()
@@ -41,8 +53,19 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         for p in params:
             p.grad = None
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._eager_step(params, zero=False)
+        n0 = _ops.N.launch_count()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._eager_step(params, zero=False)
+        except RuntimeError as e:
+            if 'legacy stream' in str(e) or 'previous error during capture' in str(e):
+                raise _ops.N.EffdetNativeError(
+                    'GraphedTrainStep: the autograd engine tried to synchronise with the legacy default stream during '
+                    'capture.  The gradient accumulators of the parameters remember the stream of an earlier eager step '
+                    'for as long as that step\'s graph is alive: drop every reference to earlier losses / outputs '
+                    '(`del loss`) before building the graphed step, or run eager steps under a side stream.') from e
+            raise
+        self.library_launches = _ops.N.launch_count() - n0            # kernels of this library recorded into the graph
         self.params = params
 
     def _eager_step(self, params, zero=True):
@@ -54,9 +77,12 @@ class GraphedTrainStep:
         # torch.autograd.grad, not .backward(): AccumulateGrad nodes remember the stream of an earlier eager step (the
         # legacy stream if the caller still holds that step's loss) and would make it wait on the capturing stream --
         # cudaErrorStreamCaptureImplicit.  The returned tensors live in the graph's pool: every replay rewrites them.
-        grads = torch.autograd.grad(loss, params, allow_unused=True)
-        for p, g in zip(params, grads):
-            p.grad = g
+        if self.ddp:
+            loss.backward()
+        else:
+            grads = torch.autograd.grad(loss, params, allow_unused=True)
+            for p, g in zip(params, grads):
+                p.grad = g
         if self.optimizer is not None:
             self.optimizer.step()
         return loss.detach()
