@@ -49,7 +49,7 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& wmap, const effd
                                              const int kblocks, const int m0, const int n0) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
@@ -336,7 +336,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_co
                        const int ntn, const int total_tiles) {
     using S = FwdSmem<BN, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* acc_full = empty_bar + STAGES;
@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 wgrad_tc_kernel(const effdet_wgrad_args p, const int M, const int HW, const int chunks_per_split, const int ctiles) {
     using S = WgSmem<BC, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
@@ -769,7 +769,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_consta
                  const WgGeom g, const int chunks_per_split, const int ctiles) {
     using S = WgSmem<BC, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;
@@ -901,7 +901,7 @@ wgrad_tc2_multi_kernel(const __grid_constant__ WgMaps maps, const __grid_constan
                        const int ctiles) {
     using S = WgSmem<BC, STAGES>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::kStage);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* accum_bar = empty_bar + STAGES;

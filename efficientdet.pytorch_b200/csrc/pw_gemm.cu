@@ -73,7 +73,7 @@ __global__ void __launch_bounds__((NC + 6) * 32, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_y, const __grid_constant__ PwParams P) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned AND still a shared-space pointer (LDS/STS, not generic LD/ST)
     const effdet_conv_args& p = P.a;
     const int a32_bytes = P.planes ? kPwA16 : P.a32_halves * kPwA32Half;
     const int b_plane = P.BN * 128;

@@ -16,12 +16,11 @@
 
 namespace effdet {
 
-constexpr int kWgConv = 8;                      // converter warps: few, with ~220 registers each -- a spilled variable shares its
-                                                // scoreboard with the prefetched loads and would wait for them (measured: 68 % long-scoreboard stalls)
-constexpr int kWgCT = kWgConv * 32;             // converter threads
-constexpr int kWgThreads = kWgCT + 32;          // + the MMA warp
-constexpr int kWgUnits = 6;                     // 8-channel units per converter thread and stage: K * (octs of x + dy) <= 1536
-
+// Two instantiations: <7 converter warps x 7 units> (256 threads, up to 255 registers: the double-buffered loads of a
+// thread keep 14 x 32 bytes in flight -- for the plain operands of the expand convs, which are latency bound) and
+// <15 x 3> (512 threads, 128 registers: twice the issue slots -- for the project convs, whose x operand needs
+// BN + swish + SE gate on every element).  A spilled variable would share its scoreboard with the prefetched loads and
+// wait for them (measured on the first version: 68 % long-scoreboard stalls), so neither variant may spill.
 struct PwWgParams {
     const float* x;
     const float* dy;
@@ -32,7 +31,7 @@ struct PwWgParams {
     float* dw;
     int M, HW, Cin, Cout;
     int ntn, NX, TM;                // input-channel tiles, their width (multiple of 16, <= 256), output channels per tile (<= 128)
-    int K;                          // pixels per stage: 32 / 64 / 128, the largest with K * (channel octets) <= 1536
+    int K;                          // pixels per stage: 16 .. 128, the largest whose units fit the converter threads
     int nchunks, cps;               // K-pixel chunks, chunks per split
     int NS, stage_bytes;            // ring depth, bytes per stage
     int a_plane, b_plane;           // bytes of one dy / x plane of a stage (1 or 2 groups of 64 channels)
@@ -46,7 +45,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_constant__ PwWgParams P) {
+template <int kWgConv, int kWgUnits>
+__global__ void __launch_bounds__(kWgConv * 32 + 32, 1) pw_wgrad_kernel(const __grid_constant__ PwWgParams P) {
+    constexpr int kWgCT = kWgConv * 32, kWgThreads = kWgCT + 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);    // 1024-byte aligned, still a shared pointer
     uint8_t* ctl = smem + P.NS * P.stage_bytes;
@@ -205,7 +206,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) pw_wgrad_kernel(const __grid_co
         tc_fence_after();
         const int quarter = warp & 3;
 #pragma unroll 1
-        for (int col = (warp >> 2) * 32; col < nmma; col += (kWgConv / 4) * 32) {    // warp-uniform
+        const int nq = (kWgConv - quarter + 3) / 4;               // converter warps that can read this lane quarter
+        for (int col = (warp >> 2) * 32; col < nmma; col += nq * 32) {    // warp-uniform
             uint32_t acc[32];
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + col, acc);
             const int r = quarter * 32 + lane;
@@ -295,7 +297,11 @@ int pw_wgrad_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     ntm = cdiv(a->Cout, P.TM);
     const int tiles = P.ntn * ntm;
     const int octs = (P.NX < a->Cin ? P.NX : a->Cin) / 8 + P.TM / 8;
-    P.K = octs <= 12 ? 128 : (octs <= 24 ? 64 : 32);             // K * octs <= 1536 units = 6 per converter thread
+    const bool heavy = a->in_scale || a->a_scale;                // per-element prologue: issue-bound -> the 15-warp variant
+    const int capacity = heavy ? 15 * 32 * 3 : 7 * 32 * 7;       // units one stage may hold
+    P.K = 128;
+    while (P.K > 16 && P.K * octs > capacity) P.K >>= 1;
+    if (P.K * octs > capacity) return fail(EFFDET_ERR_UNSUPPORTED, "wgrad(pw): tile does not fit");   // (octs <= 48: 16 * 48 = 768 always fits)
     P.nchunks = cdiv(P.M, P.K);
     int splits = 148 / tiles;
     if (splits < 1) splits = 1;
@@ -309,9 +315,16 @@ int pw_wgrad_launch(const effdet_wgrad_args* a, cudaStream_t st) {
     P.NS = (200 * 1024) / P.stage_bytes;
     if (P.NS > 4) P.NS = 4;
     const size_t smem = (size_t)P.NS * P.stage_bytes + 128 + 2 * 256 * sizeof(float) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(pw): smem opt-in: %s", cudaGetErrorString(e));
-    pw_wgrad_kernel<<<dim3(tiles, splits), kWgThreads, smem, st>>>(P);
+    cudaError_t e;
+    if (heavy) {
+        e = cudaFuncSetAttribute(pw_wgrad_kernel<15, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(pw): smem opt-in: %s", cudaGetErrorString(e));
+        pw_wgrad_kernel<15, 3><<<dim3(tiles, splits), 15 * 32 + 32, smem, st>>>(P);
+    } else {
+        e = cudaFuncSetAttribute(pw_wgrad_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(EFFDET_ERR_LAUNCH, "wgrad(pw): smem opt-in: %s", cudaGetErrorString(e));
+        pw_wgrad_kernel<7, 7><<<dim3(tiles, splits), 7 * 32 + 32, smem, st>>>(P);
+    }
     return launch_status("pw_wgrad_kernel");
 }
 

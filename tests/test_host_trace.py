@@ -265,7 +265,7 @@ def _label(name, snap):
     if name in ('effdet_conv2d', 'effdet_conv2d_wgrad'):
         a = snap[0]
         key += ' k%d %d->%d' % (a['ksize'], a['Cin'], a['Cout'])
-    elif name in ('effdet_conv2d_multi', 'effdet_conv2d_wgrad_multi'):
+    elif name in ('effdet_conv2d_multi', 'effdet_conv2d_wgrad_multi', 'effdet_conv_planes_multi'):
         a = snap[0][0]
         key += ' k%d %d->%d' % (a['ksize'], a['Cin'], a['Cout'])
     return key
