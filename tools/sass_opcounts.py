@@ -13,7 +13,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(R, 'efficientdet.pytorch_b200', 'csrc', 'libeffdet_b200.so')
 tag = sys.argv[1] if len(sys.argv) > 1 else 'r02'
 KEYS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UBLKCP', 'SYNCS', 'LDGSTS', 'HMMA', 'LDG', 'STG', 'RED', 'ATOMG',
-        'LDS', 'STS', 'MUFU', 'FFMA', 'BAR', 'LD', 'ST']      # LD / ST = generic-address loads / stores (last: prefixes)
+        'LDS', 'STS', 'MUFU', 'FFMA', 'BAR', 'LD', 'ST']      # LD / ST = generic-address loads / stores (exact match)
 out = subprocess.run(['cuobjdump', '-sass', SO], capture_output=True, text=True, check=True).stdout
 kern, counts = None, {}
 for line in out.splitlines():
@@ -28,7 +28,7 @@ for line in out.splitlines():
     if m and kern:
         op = m.group(1)
         for k in KEYS:
-            if op.startswith(k):
+            if (op == k) if k in ('LD', 'ST') else op.startswith(k):
                 counts[kern][k] += 1
                 break
 rows = sorted(counts.items(), key=lambda kv: (-kv[1]['UTCHMMA'], -kv[1]['UTMALDG'], kv[0]))
