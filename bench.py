@@ -457,7 +457,7 @@ def run_ours(args):
         else:
             det = last.get('det')
             config.update(threshold=args.threshold, iou_threshold=0.5, detections=int(det[0].numel()) if det is not None else None)
-        line = dict(metric=cfgd['metric'], value=round(imgs / (ms * 1e-3), 2), unit='img/s', n_gpus=world, steps=args.steps,
+        line = dict(impl='ours', metric=cfgd['metric'], value=round(imgs / (ms * 1e-3), 2), unit='img/s', n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32', data='synthetic', config=config,
                     clocks=sampler.summary(),
