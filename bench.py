@@ -433,7 +433,7 @@ def run_ours(args):
                               '(bf16 hi/lo split for <=1e-3 parity): tensor-pipe work = %.0f TFLOP/s = %.2f of peak'
                               % (3 * ach, 3 * ach / peak)) if tc else None,
                         launches_per_step=n // psteps, ms_per_step=round(t_ms / psteps, 3),
-                        traffic=measured_traffic('conv_planes_kernel<256> 256->256') if tc else None)
+                        traffic=measured_traffic('conv_planes_kernel<256> 256->256') if (tc and args.config == 'd0') else None)
         if not args.no_cpu and world == 1:      # the CPU leg is an N=1 measurement (the host cores are shared by all ranks)
             if train:
                 cpu_base = cpu_baseline_subprocess(args.config, 5 if args.config == 'd0' else 1, 1, 8 if args.config == 'd0' else 1,

@@ -67,8 +67,23 @@ class RetinaHead(nn.Module):
     def forward_concat_nhwc(self, feats):
         """NHWC feature maps -> (cls [B, sum(HWA), K] probabilities, reg [B, sum(HWA), 4])."""
         params = self._params()
+        K, A = self.num_classes, self.num_anchors
+        Kp = (K + 3) // 4 * 4
+        if Kp != K:
+            # the kernels move channels in vectors of 4: a class count that is not a multiple of 4 (custom datasets with
+            # 1, 3, 90 ... classes; the reference accepts any) runs with zero-weight dummy classes appended per anchor --
+            # ordinary autograd ops, so retina_cls.weight / .bias keep their reference shapes and receive their gradients
+            w, b = params[-4], params[-3]
+            wp = w.new_zeros((A, Kp) + tuple(w.shape[1:]))
+            wp[:, :K] = w.view((A, K) + tuple(w.shape[1:]))
+            bp = b.new_zeros((A, Kp))
+            bp[:, :K] = b.view(A, K)
+            params[-4], params[-3] = wp.view((A * Kp,) + tuple(w.shape[1:])), bp.view(A * Kp)
         fn = _ops.RetinaHeadPlanesFn if _ops.head_planes_ok(feats, params) else _ops.RetinaHeadFn
-        return fn.apply(len(feats), self.num_anchors, self.num_classes, self.stacked_convs, *feats, *params)
+        cls, reg = fn.apply(len(feats), A, Kp, self.stacked_convs, *feats, *params)
+        if Kp != K:
+            cls = cls[..., :K].contiguous()
+        return cls, reg
 
     def forward_concat(self, feats):
         return self.forward_concat_nhwc([_ops.to_nhwc(f, 'RetinaHead input') for f in feats])

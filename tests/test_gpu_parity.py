@@ -590,6 +590,67 @@ def test_head_planes_path_forward_backward(B, top):
     assert max(errs) < 5e-2
 
 
+@pytest.mark.parametrize('K,B,top', [(3, 4, 32), (90, 2, 16), (1, 4, 32)])
+def test_head_class_count_not_a_multiple_of_4(K, B, top):
+    """The reference accepts any num_classes; the kernels move channels in vectors of 4, so RetinaHead pads every anchor's
+    class block with zero-weight dummy classes (plain autograd ops around the fused head).  Forward, feature gradients
+    and the gradients of the UNPADDED retina_cls parameters vs the CPU oracle; planes path (top=32, B=4) and the fallback."""
+    from models.retinahead import RetinaHead
+    cfg = O.make_config('efficientdet-d0', K, 64, 2)
+    sd = O.init_state_dict(cfg, seed=35)
+    m = _load(RetinaHead(num_classes=K, in_channels=64), sd, 'bbox_head.')
+    assert tuple(m.retina_cls.weight.shape) == (9 * K, 256, 3, 3)
+    g = torch.Generator().manual_seed(8)
+    feats = [torch.randn(B, 64, top >> i, top >> i, generator=g) for i in range(5)]
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    fd = [f.to(_dev()).requires_grad_(True) for f in feats]
+    sdg = _grad_sd(sd)
+    cr, rr = O.head_forward(sdg, fr, cfg)
+    cd, rd = m(fd)
+    lr, l = 0, 0
+    for a, b in list(zip(cd, cr)) + list(zip(rd, rr)):
+        assert tuple(a.shape) == tuple(b.shape)
+        assert _rel(a.detach().cpu(), b.detach()) < 2e-4
+        wgt = torch.randn(b.shape, generator=g)
+        lr = lr + (b * wgt).sum()
+        l = l + (a * wgt.to(_dev())).sum()
+    lr.backward()
+    l.backward()
+    assert max(_rel(a.grad.cpu(), b.grad) for a, b in zip(fd, fr)) < 5e-2
+    worst = _compare_param_grads(m, sdg, 'bbox_head.', tol=5e-2)
+    print('head K=%d: worst param grad %s' % (K, worst))
+
+
+def test_model_with_three_classes_train_step_and_inference():
+    """Whole model with num_classes=3 (not a multiple of 4): train-step losses and gradients vs the oracle, then the
+    inference path (decode + NMS) returns the oracle's detections."""
+    K = 3
+    cfg = O.make_config('efficientdet-d0', num_classes=K, W_bifpn=64, D_bifpn=2)
+    sd = O.init_state_dict(cfg, seed=41)
+    m = _build('efficientdet-d0', K, 64, 2, sd, is_training=True)
+    m.eval()
+    m.is_training = True
+    images, ann = O.synthetic_batch(2, size=256, num_classes=K, seed=42)
+    cl, rl = m([images.to(_dev()), ann.to(_dev())])
+    (cl.mean() + rl.mean()).backward()
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
+    ocl, orl = O.train_forward(sdg, images, ann, cfg)
+    (ocl.mean() + orl.mean()).backward()
+    assert _rel(cl.detach().cpu(), ocl.detach()) < 1e-3 and _rel(rl.detach().cpu(), orl.detach()) < 1e-3
+    worst = 0.0
+    for k, p in m.named_parameters():
+        if sdg[k].grad is not None and float(sdg[k].grad.abs().max()) > 0:
+            worst = max(worst, _rel(p.grad.cpu(), sdg[k].grad))
+    assert worst < TOL_GRAD['bf16x3'], worst
+    assert tuple(m.bbox_head.retina_cls.weight.grad.shape) == (9 * K, 256, 3, 3)
+    m.is_training = False
+    m.threshold = 0.03
+    with torch.no_grad():
+        det = m(images[:1].to(_dev()))
+        ref = O.detect(sd, images[:1], cfg, threshold=0.03, iou_threshold=0.5)
+    assert ref[0].numel() > 0 and abs(det[0].numel() - ref[0].numel()) <= max(3, ref[0].numel() // 20)
+
+
 @pytest.mark.parametrize('empty_first', [False, True])
 def test_focal_loss_forward_backward(empty_first):
     from models.losses import FocalLoss
