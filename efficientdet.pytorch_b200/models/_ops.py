@@ -84,6 +84,16 @@ def _zeros_like_many(tensors):
     return out
 
 
+def _stash(ctx, name):
+    """Activations a fused node keeps for its backward live on ctx and are released by the first backward (the step's
+    activation memory must not outlive it).  A second backward (retain_graph=True) therefore cannot be served."""
+    v = getattr(ctx, name)
+    if v is None:
+        raise N.EffdetNativeError('backward was called a second time on a fused EfficientDet node: its saved activations are '
+                                  'released after the first backward (retain_graph=True is not supported; run forward again)')
+    return v
+
+
 # ------------------------------------------------------------------------------------------------
 # parameter-derived caches (invalidated by in-place updates: optimizer.step, load_state_dict)
 # ------------------------------------------------------------------------------------------------
@@ -435,7 +445,7 @@ class MBConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        cfg, P, t = ctx.cfg, ctx.P, ctx.t
+        cfg, P, t = ctx.cfg, ctx.P, _stash(ctx, 't')
         if t is None:
             raise RuntimeError('MBConvFn: backward called twice (activations are released after the first backward)')
         dy = _contig(dy)
@@ -626,7 +636,7 @@ class BiFPNLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *douts):
         eps, L = ctx.eps, ctx.L
-        ins, td, out, fused, w1, w2, w1c, w2c, convs = ctx.keep
+        ins, td, out, fused, w1, w2, w1c, w2c, convs = _stash(ctx, 'keep')
         douts = [_contig(d) for d in douts]
         C = ins[0].shape[3]
         zb = _zeros_like_many([w1c, w2c] + list(convs))
@@ -738,7 +748,7 @@ class RetinaHeadFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dcls, dreg):
         nl, A, K, stacked, offs, tot = ctx.meta
-        feats, P, towers, cls_all = ctx.keep
+        feats, P, towers, cls_all = _stash(ctx, 'keep')
         cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
         wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
         B = feats[0].shape[0]
@@ -892,7 +902,7 @@ class RetinaHeadPlanesFn(torch.autograd.Function):
         nl, A, K, stacked, offs, tot, geo, Cin, F = ctx.meta
         if ctx.keep is None:
             raise RuntimeError('RetinaHeadPlanesFn: backward called twice (activations are released after the first backward)')
-        P, towers, cls_all = ctx.keep
+        P, towers, cls_all = _stash(ctx, 'keep')
         cls_p, reg_p = P[:2 * stacked], P[2 * stacked:4 * stacked]
         wc, bc, wr, br = P[4 * stacked:4 * stacked + 4]
         dcls, dreg = _contig(dcls), _contig(dreg)

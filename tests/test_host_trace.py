@@ -361,6 +361,26 @@ def test_scaled_variants_issue_consistent_geometry(traced, net, W, D, size):
     assert c['effdet_focal_loss_fwd'] == 1 and c['effdet_focal_loss_bwd'] == 1 and c['effdet_stem_wgrad'] == 1
 
 
+def test_second_backward_is_refused_with_a_clear_message(traced):
+    """the fused nodes release their saved activations in the first backward; a retained graph must fail loudly, not with a
+    TypeError on None -- and class counts that are not multiples of 4 go through the padded head"""
+    rec, N = traced
+    from models import EfficientDet
+    cfg = O.make_config('efficientdet-d0', 3, 64, 2)
+    m = EfficientDet(num_classes=3, network='efficientdet-d0', D_bifpn=2, W_bifpn=64, is_training=True)
+    m.load_state_dict(O.init_state_dict(cfg, seed=2))
+    m.train()
+    m.is_training = True
+    m.freeze_bn()
+    images, ann = O.synthetic_batch(1, size=128, num_classes=3, seed=5)
+    cl, rl = m([images, ann])
+    loss = cl.mean() + rl.mean()
+    loss.backward(retain_graph=True)
+    assert tuple(m.bbox_head.retina_cls.weight.grad.shape) == (27, 256, 3, 3)      # 9 anchors x 3 classes, unpadded
+    with pytest.raises(N.EffdetNativeError, match='second time'):
+        loss.backward()
+
+
 def test_non_halving_pyramid_is_refused(traced):
     """192 = 1.5 * 128: P6 is 3x3 and P7 2x2 -- the reference dies with a shape mismatch inside BiFPNModule.forward
     (models/bifpn.py:188-201); the drop-in must refuse too instead of letting the fusion kernel index out of range"""
