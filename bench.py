@@ -64,7 +64,17 @@ def measured_traffic(kernel_key):
     p = os.path.join(REPO, 'profiles', 'r02_ncu_traffic.json')
     if not os.path.exists(p):
         return None
-    return json.load(open(p)).get(kernel_key)
+    d = json.load(open(p))
+    # the capture is only quoted for the kernel source it was taken from
+    import hashlib
+    csrc = os.path.join(REPO, 'efficientdet.pytorch_b200', 'csrc')
+    try:
+        h = hashlib.sha1(open(os.path.join(csrc, 'conv_planes.cu'), 'rb').read() + open(os.path.join(csrc, 'tc_ptx.cuh'), 'rb').read()).hexdigest()
+    except OSError:
+        return None
+    if d.get('source_sha1 (conv_planes.cu + tc_ptx.cuh)') != h:
+        return None
+    return d.get(kernel_key)
 
 
 class ClockSampler(threading.Thread):
